@@ -1,0 +1,119 @@
+"""Oracle pinning, part 1: primitives against known answers and the independent Python model."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import orc
+import pyref
+
+RFC9380_DST = b"QUUX-V01-CS02-with-expander-SHA256-128"
+
+
+def test_sha256_fips_vectors():
+    assert orc.sha256(b"abc").hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    assert orc.sha256(b"").hex() == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    m = b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq"
+    assert orc.sha256(m).hex() == "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"
+    rng = np.random.default_rng(1)
+    for n in [1, 55, 56, 63, 64, 65, 119, 120, 121, 127, 128, 129, 1000]:
+        msg = rng.bytes(n)
+        assert orc.sha256(msg) == hashlib.sha256(msg).digest()
+
+
+@pytest.mark.parametrize("msg,want", [
+    (b"", "68a985b87eb6b46952128911f2a4412bbc302a9d759667f87f7a21d803f07235"),
+    (b"abc", "d8ccab23b5985ccea865c6c97b6e5b8350e794e603b4b97902f53a8a0d605615"),
+    (b"abcdef0123456789", "eff31487c770a893cfb36f912fbfcbff40d5661771ca4b2cb4eafe524333f5c1"),
+])
+def test_xmd_rfc9380_vectors(msg, want):
+    # RFC 9380 appendix K.1 (z_pad = SHA-256 block size 64)
+    assert orc.expand_message_xmd(msg, RFC9380_DST, 32, 64).hex() == want
+    assert pyref.expand_message_xmd(msg, RFC9380_DST, 32, 64).hex() == want
+
+
+def test_xmd_ark04_variant_matches_python_model():
+    rng = np.random.default_rng(2)
+    for n in [0, 1, 33, 100, 121, 187, 300]:
+        msg = rng.bytes(n)
+        for dst in [b"ipa", b"multiproof"]:
+            assert orc.expand_message_xmd(msg, dst, 48, 48) == pyref.expand_message_xmd(msg, dst, 48, 48)
+            got = orc.buf_to_fr(orc.hash_to_fr(msg, dst.decode()))[0]
+            assert got == pyref.hash_to_fr(msg, dst)
+
+
+def test_field_ops_match_python_ints():
+    rng = np.random.default_rng(3)
+    for tag, mod, enc, dec in [(0, orc.R_MOD, orc.fr_to_buf, orc.buf_to_fr), (1, orc.P_MOD, orc.fq_to_buf, orc.buf_to_fq)]:
+        xs = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(64)] + [0, 1, mod - 1, mod - 2]
+        ys = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(64)] + [mod - 1, 0, mod - 1, 2]
+        a, b = enc(xs), enc(ys)
+        assert dec(orc.field_op(tag, "add", a, b)) == [(x + y) % mod for x, y in zip(xs, ys)]
+        assert dec(orc.field_op(tag, "sub", a, b)) == [(x - y) % mod for x, y in zip(xs, ys)]
+        assert dec(orc.field_op(tag, "mul", a, b)) == [(x * y) % mod for x, y in zip(xs, ys)]
+        nz = [x for x in xs if x]
+        assert dec(orc.field_op(tag, "inv", enc(nz))) == [pow(x, -1, mod) for x in nz]
+        # Montgomery conversion round trip against the pure-python encoder
+        canon = np.stack([np.frombuffer(x.to_bytes(32, "little"), dtype=np.uint8) for x in xs])
+        assert (orc.to_mont(tag, canon) == a).all()
+        assert (orc.from_mont(tag, a) == canon).all()
+
+
+def test_montgomery_constants_from_survey():
+    # R mod r and R mod p
+    assert orc.MONT_R % orc.R_MOD == 0x0e0a77c19a07df2f666ea36f7879462e36fc76959f60cd29ac96341c4ffffffb
+    assert orc.MONT_R % orc.P_MOD == 0x0e0a77c19a07df2f666ea36f7879462c0a78eb28f5c70b3dd35d438dc58f0d9d
+    one = orc.fr_to_buf([1])[0]
+    assert int.from_bytes(bytes(one), "little") == orc.MONT_R % orc.R_MOD
+
+
+def test_g1_known_multiples():
+    # alt_bn128 2G (EIP-196 test vectors)
+    g = orc.g1_generator()
+    assert orc.buf_to_pts(g) == [(1, 2)]
+    two_g = orc.buf_to_pts(orc.g1_add(g, g))[0]
+    assert two_g == (0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3,
+                     0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4)
+    assert two_g == pyref.g_add(pyref.G1_GEN, pyref.G1_GEN)
+    # r * G = identity, (r-1) G = -G
+    assert orc.buf_to_pts(orc.g1_mul(g, orc.fr_to_buf([orc.R_MOD - 1])))[0] == (1, orc.P_MOD - 2)
+    assert orc.buf_to_pts(orc.g1_add(orc.g1_mul(g, orc.fr_to_buf([orc.R_MOD - 1])), g))[0] is None
+
+
+def test_g1_group_law_matches_python_model():
+    rng = np.random.default_rng(4)
+    ks = orc.rand_fr(rng, 12) + [0, 1, 2, orc.R_MOD - 1]
+    pts = [pyref.g_mul(pyref.G1_GEN, k) for k in ks]
+    bufs = orc.pts_to_buf(pts)
+    got = orc.buf_to_pts(orc.g1_mul_gen_batch(orc.fr_to_buf(ks), 2))
+    assert got == pts
+    for i in range(len(pts)):
+        for j in [0, 3, len(pts) - 1, i]:
+            assert orc.buf_to_pts(orc.g1_add(bufs[i], bufs[j]))[0] == pyref.g_add(pts[i], pts[j])
+        assert orc.g1_on_curve(bufs[i])
+    walk = orc.buf_to_pts(orc.points_walk(ks[0], ks[1], 5))
+    assert walk == [pyref.g_mul(pyref.G1_GEN, ks[0] + i * ks[1]) for i in range(5)]
+
+
+def test_compressed_serialisation_and_to_data_item():
+    rng = np.random.default_rng(5)
+    ks = orc.rand_fr(rng, 16)
+    pts = [pyref.g_mul(pyref.G1_GEN, k) for k in ks] + [None, pyref.G1_GEN, pyref.g_neg(pyref.G1_GEN)]
+    buf = orc.pts_to_buf(pts)
+    comp = orc.g1_compress(buf)
+    for row, p in zip(comp, pts):
+        assert bytes(row) == pyref.ser_g1(p)
+    # generator: y = 2 <= p - 2  -> no flag ; -G -> 0x80 ; infinity -> 0x40
+    assert bytes(comp[-2]) == (1).to_bytes(32, "little")
+    assert comp[-1][31] == 0x80 and comp[-3][31] == 0x40
+    assert orc.buf_to_fr(orc.to_data_item(buf)) == [pyref.to_data_item(p) for p in pts]
+
+
+def test_domain_generators():
+    # SURVEY.md section 8 constants
+    assert orc.buf_to_fr(orc.domain_gen(256))[0] == 3478517300119284901893091970156912948790432420133812234316178878452092729974
+    assert orc.buf_to_fr(orc.domain_gen(32))[0] == 4419234939496763621076330863786513495701855246241724391626358375488475697872
+    assert pyref.group_gen(256) == 3478517300119284901893091970156912948790432420133812234316178878452092729974
+    w = pyref.group_gen(256)
+    assert pow(w, 256, pyref.R_MOD) == 1 and pow(w, 128, pyref.R_MOD) != 1
+    assert orc.buf_to_fr(orc.domain_gen(20))[0] == pyref.group_gen(32)
