@@ -1,0 +1,152 @@
+"""Product arithmetic headers (csrc/field.cuh, curve.cuh, hash.cuh) executed on the CPU through
+tests/host/libhostcheck.so and compared with Python ints / hashlib / the oracle.  The carry-chain
+primitives are host-emulated; everything above them is the code the kernels run."""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+import pyref
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(_DIR, "libhostcheck.so")
+    subprocess.check_call(["make", "-C", _DIR, "libhostcheck.so"], stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _op(hc, tag, op, a, b=None):
+    out = np.zeros_like(a)
+    hc.hc_field_op(tag, op, _p(a), None if b is None else _p(b), _p(out), ctypes.c_uint64(len(a)))
+    return out
+
+
+@pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
+def test_field_ops(hc, tag, mod):
+    rng = np.random.default_rng(100 + tag)
+    enc, dec = (orc.fr_to_buf, orc.buf_to_fr) if tag == 0 else (orc.fq_to_buf, orc.buf_to_fq)
+    edge = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 2 ** 253, 2 ** 32 - 1, 2 ** 224 - 1]
+    xs = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(400)] + edge + edge
+    ys = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(400)] + edge + edge[::-1]
+    a, b = enc(xs), enc(ys)
+    assert dec(_op(hc, tag, 0, a, b)) == [(x + y) % mod for x, y in zip(xs, ys)]
+    assert dec(_op(hc, tag, 1, a, b)) == [(x - y) % mod for x, y in zip(xs, ys)]
+    assert dec(_op(hc, tag, 2, a, b)) == [(x * y) % mod for x, y in zip(xs, ys)]
+    assert dec(_op(hc, tag, 6, a)) == [(-x) % mod for x in xs]
+    nz = [x for x in xs[:40] + edge if x]
+    assert dec(_op(hc, tag, 3, enc(nz))) == [pow(x, -1, mod) for x in nz]
+    # from_mont gives the canonical integer; to_mont inverts it
+    canon = _op(hc, tag, 4, a)
+    assert [int.from_bytes(bytes(r), "little") for r in canon] == xs
+    assert (_op(hc, tag, 5, canon) == a).all()
+    # worst-case limbs for the carry chains: raw Montgomery representations with all-ones limbs (< p)
+    raw = np.full((4, 32), 0xFF, dtype=np.uint8)
+    raw[:, 31] = [0x2F, 0x30, 0x1F, 0x00]
+    raw[1, 28:31] = [0, 0, 0]
+    ints = [int.from_bytes(bytes(r), "little") for r in raw]
+    assert all(v < mod for v in ints)
+    rinv = pow(orc.MONT_R, -1, mod)
+    got = _op(hc, tag, 2, raw, raw[::-1].copy())
+    want = [(x * y * rinv) % mod for x, y in zip(ints, ints[::-1])]
+    assert [int.from_bytes(bytes(r), "little") for r in got] == want
+
+
+def test_group_ops(hc):
+    rng = np.random.default_rng(7)
+    ks = orc.rand_fr(rng, 6) + [1, 2]
+    pts = [pyref.g_mul(pyref.G1_GEN, k) for k in ks] + [None]
+    buf = orc.pts_to_buf(pts)
+    out = np.zeros(64, dtype=np.uint8)
+    for i in range(len(pts)):
+        for j in range(len(pts)):
+            for mode in (0, 1):
+                hc.hc_g1_op(mode, _p(buf[i]), _p(buf[j]), _p(out))
+                assert orc.buf_to_pts(out)[0] == pyref.g_add(pts[i], pts[j]), (mode, i, j)
+        hc.hc_g1_op(2, _p(buf[i]), _p(buf[i]), _p(out))
+        assert orc.buf_to_pts(out)[0] == pyref.g_add(pts[i], pts[i])
+        # P + (-P) -> infinity, then + again
+        neg = orc.pts_to_buf([pyref.g_neg(pts[i])])[0]
+        hc.hc_g1_op(0, _p(buf[i]), _p(neg), _p(out))
+        assert orc.buf_to_pts(out)[0] is None
+        hc.hc_g1_op(3, _p(buf[i]), _p(buf[(i + 1) % len(pts)]), _p(out))
+        assert orc.buf_to_pts(out)[0] == pyref.g_add(pts[i], pts[(i + 1) % len(pts)])
+
+
+@pytest.mark.parametrize("c", [4, 8, 13, 16, 20])
+def test_signed_window_recoding_msm(hc, c):
+    rng = np.random.default_rng(200 + c)
+    n = 6
+    bases = orc.points_walk(*orc.rand_fr(rng, 2), n)
+    s = orc.rand_fr(rng, n)
+    s[0], s[1], s[2] = orc.R_MOD - 1, 0, (1 << (c - 1))
+    s[3] = int("1" * 254, 2) % orc.R_MOD
+    sb = orc.fr_to_buf(s)
+    out = np.zeros(64, dtype=np.uint8)
+    hc.hc_msm_windowed(_p(bases), _p(sb), ctypes.c_uint64(n), c, _p(out))
+    assert (out == orc.msm(bases, sb, "naive", 2)).all()
+
+
+def test_compress_and_hashing(hc):
+    rng = np.random.default_rng(9)
+    pts = [pyref.g_mul(pyref.G1_GEN, k) for k in orc.rand_fr(rng, 8)] + [None, pyref.G1_GEN, pyref.g_neg(pyref.G1_GEN)]
+    buf = orc.pts_to_buf(pts)
+    out = np.zeros((len(pts), 32), dtype=np.uint8)
+    hc.hc_compress(_p(buf), ctypes.c_uint64(len(pts)), _p(out))
+    assert [bytes(r) for r in out] == [pyref.ser_g1(p) for p in pts]
+    d = np.zeros(32, dtype=np.uint8)
+    for n in [0, 1, 55, 56, 63, 64, 65, 100, 119, 120, 128, 187, 249]:
+        msg = np.frombuffer(rng.bytes(max(n, 1)), dtype=np.uint8).copy()
+        hc.hc_sha256(_p(msg), n, _p(d))
+        assert bytes(d) == hashlib.sha256(bytes(msg[:n])).digest()
+        for dst in [b"ipa", b"multiproof"]:
+            dd = np.frombuffer(dst, dtype=np.uint8).copy()
+            u = np.zeros(48, dtype=np.uint8)
+            hc.hc_xmd48(_p(msg), n, _p(dd), len(dst), 48, _p(u))
+            assert bytes(u) == pyref.expand_message_xmd(bytes(msg[:n]), dst, 48, 48)
+            f = np.zeros(32, dtype=np.uint8)
+            hc.hc_hash_to_fr(_p(msg), n, _p(dd), len(dst), _p(f))
+            assert orc.buf_to_fr(f)[0] == pyref.hash_to_fr(bytes(msg[:n]), dst)
+    # the 48-byte expansion also matches the model at the RFC's z_pad = 64
+    dd = np.frombuffer(b"QUUX-V01-CS02-with-expander-SHA256-128", dtype=np.uint8).copy()
+    u = np.zeros(48, dtype=np.uint8)
+    m = np.frombuffer(b"abc", dtype=np.uint8).copy()
+    hc.hc_xmd48(_p(m), 3, _p(dd), len(dd), 64, _p(u))
+    assert bytes(u) == pyref.expand_message_xmd(b"abc", bytes(dd), 48, 64)
+    # from_le_bytes_mod_order on 32 bytes with flag bits set (to_data_item, quirk Q7)
+    for _ in range(8):
+        raw = np.frombuffer(rng.bytes(32), dtype=np.uint8).copy()
+        f = np.zeros(32, dtype=np.uint8)
+        hc.hc_fr_from_le32(_p(raw), _p(f))
+        assert orc.buf_to_fr(f)[0] == int.from_bytes(bytes(raw), "little") % orc.R_MOD
+
+
+def test_transcript_walk(hc):
+    rng = np.random.default_rng(10)
+    ks = orc.rand_fr(rng, 3)
+    C, L, R = [pyref.g_mul(pyref.G1_GEN, k) for k in ks]
+    z, y = orc.rand_fr(rng, 2)
+    for prefix, dst in [(b"", "ipa"), (bytes(range(66)), "multiproof")]:
+        tr = pyref.Transcript(dst, prefix)
+        tr.append_g(C, "C")
+        tr.append_f(z, "input point")
+        tr.append_f(y, "output point")
+        w = tr.digest("w")
+        tr.append_g(L, "L")
+        tr.append_g(R, "R")
+        x = tr.digest("x")
+        wo, xo = np.zeros(32, dtype=np.uint8), np.zeros(32, dtype=np.uint8)
+        pre = np.frombuffer(prefix, dtype=np.uint8).copy() if prefix else np.zeros(1, dtype=np.uint8)
+        hc.hc_transcript_ipa(_p(pre), len(prefix), dst.encode(), _p(orc.pts_to_buf([C])), _p(orc.fr_to_buf([z])), _p(orc.fr_to_buf([y])),
+                             _p(orc.pts_to_buf([L])), _p(orc.pts_to_buf([R])), _p(wo), _p(xo))
+        assert orc.buf_to_fr(wo)[0] == w and orc.buf_to_fr(xo)[0] == x

@@ -1,0 +1,424 @@
+// BN254 Fr / Fq arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form with R = 2^256
+// (bit-identical in memory to arkworks' 4 x u64 MontBackend).
+//
+// The multiplier is an operand-scanning Montgomery product that keeps the running total split over
+// two limb arrays whose 64-bit (lo,hi) pairs sit at even / odd 32-bit columns, so every partial
+// product a[j]*b[i] is ONE mad.lo.cc/madc.hi.cc pair on an aligned register pair (ptxas fuses the
+// pair into IMAD.WIDE.U32[.X]) and a row consists of two independent carry chains of four such
+// pairs.  The 32-bit right shift of the running total after each reduction step is a swap of the
+// two arrays' roles, not a data move.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define VK_HD __host__ __device__ __forceinline__
+
+namespace vk {
+
+struct alignas(16) fp_t {
+    uint32_t l[8];
+};
+
+struct FrParams {
+    static constexpr uint32_t INV = 0xefffffffu;
+    VK_HD static constexpr uint32_t p(int i) {
+        constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t r1(int i) {
+        constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t half(int i) {  // (p-1)/2
+        constexpr uint32_t v[8] = {0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+        return v[i];
+    }
+};
+
+struct FqParams {
+    static constexpr uint32_t INV = 0xe4866389u;
+    VK_HD static constexpr uint32_t p(int i) {
+        constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t r1(int i) {
+        constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t half(int i) {
+        constexpr uint32_t v[8] = {0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+        return v[i];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain building blocks.  Device: one PTX asm block per chain (self-contained w.r.t. the CC
+// flag).  Host: the same semantics emulated with 64-bit arithmetic, so that every function in this
+// header can be unit-tested on a CPU (tests/host/) with the identical control flow.
+// ---------------------------------------------------------------------------------------------
+#ifndef __CUDA_ARCH__
+VK_HD void host_mad_pair(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t addlo, uint32_t addhi, uint32_t& carry) {
+    // (carry, hi, lo) = a*b + (addhi:addlo) + carry   with carries propagated like mad.lo.cc / madc.hi.cc
+    uint64_t prod = (uint64_t)a * b;
+    uint64_t l = (uint64_t)(uint32_t)prod + addlo + carry;
+    uint64_t h = (prod >> 32) + addhi + (l >> 32);
+    lo = (uint32_t)l;
+    hi = (uint32_t)h;
+    carry = (uint32_t)(h >> 32);
+}
+#endif
+
+// acc[0..7] += {a0,a2,a4,a6} * b at 64-bit column pairs (0,1),(2,3),(4,5),(6,7); top += carry-out
+VK_HD void mad_row4(uint32_t* acc, uint32_t& top, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+#else
+    uint32_t c = 0;
+    host_mad_pair(acc[0], acc[1], a0, b, acc[0], acc[1], c);
+    host_mad_pair(acc[2], acc[3], a2, b, acc[2], acc[3], c);
+    host_mad_pair(acc[4], acc[5], a4, b, acc[4], acc[5], c);
+    host_mad_pair(acc[6], acc[7], a6, b, acc[6], acc[7], c);
+    top += c;
+#endif
+}
+
+// Same, without a carry-out (caller guarantees none can occur).
+VK_HD void mad_row4_nc(uint32_t* acc, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+#else
+    uint32_t c = 0;
+    host_mad_pair(acc[0], acc[1], a0, b, acc[0], acc[1], c);
+    host_mad_pair(acc[2], acc[3], a2, b, acc[2], acc[3], c);
+    host_mad_pair(acc[4], acc[5], a4, b, acc[4], acc[5], c);
+    host_mad_pair(acc[6], acc[7], a6, b, acc[6], acc[7], c);
+#endif
+}
+
+// Row entry after a role swap:  x0 += e1 (column 0), the carry continues into the column-1 chain
+//   y[k,k+1] = e[k+2,k+3] + a_odd * b    for k = 0,2,4 ;   y[6,7] = a7 * b + carry
+// where e[] is the array whose column 0 was just cleared by the reduction step.
+VK_HD void shift_mad_row4(uint32_t& x0, uint32_t* y, const uint32_t* e, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7,
+                          uint32_t b) {
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "madc.lo.cc.u32 %1, %16, %20, %10;\n\t"
+        "madc.hi.cc.u32 %2, %16, %20, %11;\n\t"
+        "madc.lo.cc.u32 %3, %17, %20, %12;\n\t"
+        "madc.hi.cc.u32 %4, %17, %20, %13;\n\t"
+        "madc.lo.cc.u32 %5, %18, %20, %14;\n\t"
+        "madc.hi.cc.u32 %6, %18, %20, %15;\n\t"
+        "madc.lo.cc.u32 %7, %19, %20, 0;\n\t"
+        "madc.hi.u32 %8, %19, %20, 0;"
+        : "+r"(x0), "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
+#else
+    uint64_t s = (uint64_t)x0 + e[1];
+    x0 = (uint32_t)s;
+    uint32_t c = (uint32_t)(s >> 32);
+    host_mad_pair(y[0], y[1], a1, b, e[2], e[3], c);
+    host_mad_pair(y[2], y[3], a3, b, e[4], e[5], c);
+    host_mad_pair(y[4], y[5], a5, b, e[6], e[7], c);
+    host_mad_pair(y[6], y[7], a7, b, 0, 0, c);
+#endif
+}
+
+// r[0..7] = a[0..7] + b[0..7], returns the carry-out
+VK_HD uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t carry;
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(carry)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]),
+          "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    carry = (uint32_t)c;
+#endif
+    return carry;
+}
+
+// r[0..7] = a[0..7] - b[0..7], returns 0xffffffff on borrow-out else 0
+VK_HD uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t borrow;
+#ifdef __CUDA_ARCH__
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(borrow)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]),
+          "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    uint32_t bw = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - bw;
+        r[i] = (uint32_t)d;
+        bw = (uint32_t)(d >> 32) & 1;
+    }
+    borrow = bw ? 0xffffffffu : 0u;
+#endif
+    return borrow;
+}
+
+// (carry : r) >= p ?  r -= p   — r < 2p, carry is the 9th limb (0 or 1)
+template <class P>
+VK_HD void fp_cond_sub_p(uint32_t* r, uint32_t carry) {
+    uint32_t d[8], pl[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pl[k] = P::p(k);
+    uint32_t borrow = sub8(d, r, pl);
+    // keep r only if the subtraction borrowed AND there was no 9th-limb carry
+    bool keep = (borrow != 0) && (carry == 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = keep ? r[k] : d[k];
+}
+
+template <class P>
+VK_HD void reduce_step(uint32_t* x, uint32_t* y) {
+    // m = x[0] * (-p^-1) ;  total += m * p  -> x[0] becomes 0
+    uint32_t m = x[0] * P::INV;
+    mad_row4_nc(y, P::p(1), P::p(3), P::p(5), P::p(7), m);
+    mad_row4(x, y[7], P::p(0), P::p(2), P::p(4), P::p(6), m);
+}
+
+// r = a * b * R^-1 mod p, fully reduced to [0, p).  Requires a < p; b may be ANY 256-bit value (the running
+// total stays below a + p < 2p, which is what the no-carry-out chains rely on).
+template <class P>
+VK_HD fp_t fp_mul(const fp_t& a, const fp_t& b) {
+    uint32_t u[8], v[8];
+    // row 0: u (column-0 aligned) = even limbs of a times b0, v (column-1 aligned) = odd limbs
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        uint64_t t0 = (uint64_t)a.l[j] * b.l[0];
+        uint64_t t1 = (uint64_t)a.l[j + 1] * b.l[0];
+        u[j] = (uint32_t)t0;
+        u[j + 1] = (uint32_t)(t0 >> 32);
+        v[j] = (uint32_t)t1;
+        v[j + 1] = (uint32_t)(t1 >> 32);
+    }
+    reduce_step<P>(u, v);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        // roles swap: v becomes the column-0 array, a fresh column-1 array y is built from u >> 64
+        {
+            uint32_t y[8];
+            shift_mad_row4(v[0], y, u, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+            mad_row4(v, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+            reduce_step<P>(v, y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = y[k];
+        }
+        if (i + 1 < 8) {
+            uint32_t y[8];
+            shift_mad_row4(u[0], y, v, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i + 1]);
+            mad_row4(u, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i + 1]);
+            reduce_step<P>(u, y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = y[k];
+        }
+    }
+    // now v is the column-0 array with v[0] == 0 and u the column-1 array:  result = (v >> 32) + u  (< 2p)
+    uint32_t vs[8];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) vs[k] = v[k + 1];
+    vs[7] = 0;
+    fp_t r;
+    add8(r.l, u, vs);
+    fp_cond_sub_p<P>(r.l, 0);
+    return r;
+}
+
+template <class P>
+VK_HD fp_t fp_sqr(const fp_t& a) {
+    return fp_mul<P>(a, a);
+}
+
+template <class P>
+VK_HD fp_t fp_add(const fp_t& a, const fp_t& b) {
+    fp_t r;
+    uint32_t carry = add8(r.l, a.l, b.l);
+    fp_cond_sub_p<P>(r.l, carry);
+    return r;
+}
+
+template <class P>
+VK_HD fp_t fp_sub(const fp_t& a, const fp_t& b) {
+    fp_t r;
+    uint32_t borrow = sub8(r.l, a.l, b.l);
+    uint32_t pm[8], t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pm[k] = borrow & P::p(k);
+    add8(t, r.l, pm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = t[k];
+    return r;
+}
+
+template <class P>
+VK_HD fp_t fp_zero() {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = 0;
+    return r;
+}
+template <class P>
+VK_HD fp_t fp_one() {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = P::r1(i);
+    return r;
+}
+VK_HD bool fp_is_zero(const fp_t& a) {
+    return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0;
+}
+VK_HD bool fp_eq(const fp_t& a, const fp_t& b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d |= a.l[i] ^ b.l[i];
+    return d == 0;
+}
+template <class P>
+VK_HD fp_t fp_neg(const fp_t& a) {
+    return fp_sub<P>(fp_zero<P>(), a);
+}
+template <class P>
+VK_HD fp_t fp_dbl(const fp_t& a) {
+    return fp_add<P>(a, a);
+}
+// Montgomery -> canonical integer
+template <class P>
+VK_HD fp_t fp_from_mont(const fp_t& a) {
+    fp_t one;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) one.l[i] = (i == 0);
+    return fp_mul<P>(a, one);
+}
+// canonical integer (< p) -> Montgomery
+template <class P>
+VK_HD fp_t fp_to_mont(const fp_t& a) {
+    fp_t r2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r2.l[i] = P::r2(i);
+    return fp_mul<P>(a, r2);
+}
+template <class P>
+VK_HD fp_t fp_from_u32(uint32_t x) {
+    fp_t a;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.l[i] = (i == 0) ? x : 0;
+    return fp_to_mont<P>(a);
+}
+// lexicographic compare of raw limb arrays (use on canonical values): a > b
+VK_HD bool limbs_gt(const uint32_t* a, const uint32_t* b) {
+    bool gt = false, decided = false;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (!decided && a[i] != b[i]) {
+            gt = a[i] > b[i];
+            decided = true;
+        }
+    }
+    return gt;
+}
+// canonical(a) > (p-1)/2   (ark-ec SWFlags::from_y_coordinate: y > -y)
+template <class P>
+VK_HD bool fp_is_lexicographically_largest(const fp_t& a_mont) {
+    fp_t c = fp_from_mont<P>(a_mont);
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = P::half(i);
+    return limbs_gt(c.l, h);
+}
+
+// Out-of-line multiply for cold paths (keeps code size down where throughput does not matter).
+template <class P>
+__host__ __device__ __noinline__ fp_t fp_mul_ni(const fp_t a, const fp_t b) {
+    return fp_mul<P>(a, b);
+}
+
+// a^(p-2): Fermat inversion (0 -> 0).  Uniform control flow; ~256 squarings + ~130 multiplies.
+template <class P>
+__host__ __device__ __noinline__ fp_t fp_inv(const fp_t a) {
+    fp_t acc = fp_one<P>();
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        const uint32_t e = P::p(k) - (k == 0 ? 2u : 0u);  // p[0] >= 2 for both moduli
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            acc = fp_mul_ni<P>(acc, acc);
+            if ((e >> b) & 1) acc = fp_mul_ni<P>(acc, a);
+        }
+    }
+    return acc;
+}
+
+// 16-byte vector load/store of a field element (global or shared, 16-byte aligned)
+VK_HD fp_t fp_load(const fp_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fp_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ fp_t fp_load_ro(const fp_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fp_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+VK_HD void fp_store(fp_t* p, const fp_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+}  // namespace vk
