@@ -1,0 +1,178 @@
+/*
+ * vkzg.h — C ABI of libvkzg.so: the B200 (sm_100a) implementation of the vector-commitment hot path of
+ * SleepingShell/verkle-kzg.  The reference has no FFI; its operator interface for this path is the pair
+ * of Rust traits VectorCommitment (vector-commit/src/lib.rs:70-174) and VectorCommitmentMultiproof
+ * (vector-commit/src/multiproof.rs:90-216).  Each entry point below names the trait method / function
+ * whose body it replaces.  INTEGRATION.md shows the Rust `extern "C"` block and the trait impls that
+ * bind them.
+ *
+ * Conventions
+ *   - every function returns a status: 0 = ok, < 0 = error (vkzg_strerror); nothing throws across
+ *     the boundary; the caller owns every buffer; host-pointer calls return after the result is in
+ *     the caller's buffer; `_dev` calls take DEVICE pointers, enqueue on the context's stream and
+ *     return without synchronising.
+ *   - field elements (vkzg_fr / vkzg_fq): 8 little-endian u32 limbs holding the MONTGOMERY form with
+ *     R = 2^256 — byte-identical to ark-ff 0.4 `Fp<MontBackend<_,4>>` (4 x u64), so a
+ *     `&[Fr]` can be passed as `*const vkzg_fr` with no conversion.
+ *   - points (vkzg_g1_affine): x || y, 64 bytes, (0,0) encodes the point at infinity (ark-ec
+ *     `Affine::identity()` has `infinity = true`; the shim maps it).  All point results are canonical
+ *     affine coordinates, hence independent of any internal representation or summation order.
+ *   - one vkzg_ctx per host thread and per GPU (or externally synchronised).
+ *   - there is NO CPU fallback: every call fails with VKZG_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef VKZG_H
+#define VKZG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vkzg_ctx vkzg_ctx;
+typedef struct { uint32_t l[8]; } vkzg_fr;
+typedef struct { uint32_t l[8]; } vkzg_fq;
+typedef struct { vkzg_fq x, y; } vkzg_g1_affine;
+
+enum {
+    VKZG_OK = 0,
+    VKZG_ERR_CUDA = -1,        /* a CUDA call failed / no device                                           */
+    VKZG_ERR_ARG = -2,         /* null pointer, zero size, bad key id                                      */
+    VKZG_ERR_RANGE = -3,       /* index / width outside the key (reference: panic or Err(OutOfCRS))        */
+    VKZG_ERR_UNSUPPORTED = -4, /* e.g. width not a power of two for IPA (reference: unwrap on odd split)   */
+    VKZG_ERR_OOM = -5
+};
+
+/* key kinds (vkzg_key_load `kind`) */
+enum {
+    VKZG_KEY_WINDOW = 1, /* fixed-base signed-window tables for every base: batched width-N commits, IPA, KZG opens */
+    VKZG_KEY_MSM = 2     /* 2^(c*w) multiples of every base: one large shared-bucket Pippenger MSM                   */
+};
+
+const char* vkzg_strerror(int32_t status);
+uint32_t vkzg_abi_version(void);
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int32_t vkzg_ctx_create(vkzg_ctx** out, int32_t device_id);
+/* same, but all work is enqueued on the caller's cudaStream_t (e.g. torch's current stream) */
+int32_t vkzg_ctx_create_on_stream(vkzg_ctx** out, int32_t device_id, void* cuda_stream);
+int32_t vkzg_ctx_destroy(vkzg_ctx* ctx);
+int32_t vkzg_ctx_sync(vkzg_ctx* ctx);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t vkzg_ctx_launches(const vkzg_ctx* ctx);
+
+/* ---- keys: KZGKey.lagrange_commitments (kzg/mod.rs:27-57) / IPAUniversalParams{g,q} (ipa/mod.rs:22-52) --- */
+/* `q` may be NULL (KZG).  window_bits = 0 picks the default (16 for VKZG_KEY_WINDOW, by size for MSM).      */
+int32_t vkzg_key_load(vkzg_ctx* ctx, const vkzg_g1_affine* bases, uint32_t n, const vkzg_g1_affine* q,
+                      uint32_t kind, uint32_t window_bits, uint32_t* key_id);
+int32_t vkzg_key_load_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_bases, uint32_t n, const vkzg_g1_affine* d_q,
+                          uint32_t kind, uint32_t window_bits, uint32_t* key_id);
+int32_t vkzg_key_free(vkzg_ctx* ctx, uint32_t key_id);
+uint64_t vkzg_key_table_bytes(const vkzg_ctx* ctx, uint32_t key_id);
+
+/* ---- M1: utils::inner_product G x F (utils.rs:16-19) as used by KZG::commit (kzg/mod.rs:126-134) and
+ *      IPA::commit (ipa/mod.rs:130-135) ------------------------------------------------------------------- */
+/* one large MSM over the first n bases of a VKZG_KEY_MSM key (n <= key size: zip truncation, quirk Q1) */
+int32_t vkzg_msm(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* scalars, uint64_t n, vkzg_g1_affine* out);
+int32_t vkzg_msm_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_scalars, uint64_t n, vkzg_g1_affine* d_out);
+/* same over the slice [first, first + n) of the key's bases (point-range sharding across GPUs) */
+int32_t vkzg_msm_range_dev(vkzg_ctx* ctx, uint32_t key_id, uint64_t first, const vkzg_fr* d_scalars, uint64_t n,
+                           vkzg_g1_affine* d_out);
+/* B independent commits of width w (w <= key size) — scalars[B][w] -> out[B] */
+int32_t vkzg_commit_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* scalars, uint32_t w, uint64_t B,
+                          vkzg_g1_affine* out);
+int32_t vkzg_commit_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_scalars, uint32_t w, uint64_t B,
+                              vkzg_g1_affine* d_out);
+/* sum of n points (the combine step after an all-gather of per-rank partial commitments) */
+int32_t vkzg_g1_sum_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_points, uint64_t n, vkzg_g1_affine* d_out);
+int32_t vkzg_g1_sum(vkzg_ctx* ctx, const vkzg_g1_affine* points, uint64_t n, vkzg_g1_affine* out);
+
+/* ---- D1: VCCommitment::to_data_item (vector-commit/src/lib.rs:56-67) -------------------------------- */
+int32_t vkzg_to_data_item(vkzg_ctx* ctx, const vkzg_g1_affine* points, uint64_t n, vkzg_fr* out);
+int32_t vkzg_to_data_item_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_points, uint64_t n, vkzg_fr* d_out);
+
+/* ---- B1 / E1 / K1 / K2: precompute.rs:72-90, lagrange_basis.rs:63-83, :91-119, :121-142 ---------------- */
+/* barycentric coefficients of B points over the key's domain (size N): out[B][N] */
+int32_t vkzg_barycentric_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* points, uint64_t B, vkzg_fr* out);
+/* Data rows f[B][len] hold len <= N evaluations.  domain_n = 0: LagrangeBasis::from_vec(data), whose own
+ * domain has size Dn = next_pow2(len) (lagrange_basis.rs:152-155); domain_n != 0:
+ * from_vec_and_domain(data, D::new(domain_n)) (lagrange_basis.rs:24-31, as the reference's KZG tests do with
+ * the key's domain), Dn = next_pow2(domain_n).  The key's precompute has size N; the reference indexes
+ * out of bounds unless Dn <= N (VKZG_ERR_UNSUPPORTED otherwise).                                            */
+/* f(z) with the reference's 3-way branch (quirk Q2): out[B] */
+int32_t vkzg_evaluate_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n,
+                            const vkzg_fr* points, uint64_t B, vkzg_fr* out);
+/* quotient (f - f(z)) / (X - z) in evaluation form as KZG::prove_point selects it: in-domain branch for
+ * z <= N (z == N, or z >= Dn, is the reference's out-of-bounds panic -> VKZG_ERR_RANGE), outside-domain
+ * branch otherwise.  out[B][Dn], y[B]                                                                        */
+int32_t vkzg_quotient_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n,
+                            const vkzg_fr* points, uint64_t B, vkzg_fr* out, vkzg_fr* y);
+
+/* ---- K3: KZG::prove_point (kzg/mod.rs:136-154), batched over B openings ------------------------------ */
+int32_t vkzg_kzg_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f /*[B][len]*/, uint32_t len, uint32_t domain_n,
+                            const vkzg_fr* points /*[B]*/, uint64_t B, vkzg_g1_affine* proof /*[B]*/, vkzg_fr* y /*[B]*/);
+/* device-pointer variant: rows that hit the reference's panic get the identity as proof (no status) */
+int32_t vkzg_kzg_open_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
+                                const vkzg_fr* d_points, uint64_t B, vkzg_g1_affine* d_proof, vkzg_fr* d_y);
+
+/* ---- I1: IPA::prove_point + low_level_ipa (ipa/mod.rs:137-154, :268-319), batched -------------------- */
+/* a[B][N], points[B], commitments[B].  `prefix` (may be NULL) is the byte state of an in-flight transcript
+ * shared by all B proofs (lib.rs:127-133 / multiproof.rs:174), `dst` the transcript's domain label
+ * (NULL = "ipa").  Outputs: L[B][log2 N], R[B][log2 N], tip[B], y[B].                                       */
+int32_t vkzg_ipa_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, const vkzg_fr* points,
+                             const vkzg_g1_affine* commitments, uint64_t B, const uint8_t* prefix, uint32_t prefix_len,
+                             const char* dst, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* y);
+int32_t vkzg_ipa_prove_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_a, const vkzg_fr* d_points,
+                                 const vkzg_g1_affine* d_commitments, uint64_t B, const uint8_t* prefix, uint32_t prefix_len,
+                                 const char* dst, vkzg_g1_affine* d_L, vkzg_g1_affine* d_R, vkzg_fr* d_tip, vkzg_fr* d_y);
+/* ---- I3: IPA::verify_point + low_level_verify_ipa (ipa/mod.rs:165-181, :321-360), batched ------------ */
+/* ok[B] receives 1 (valid) / 0 (invalid) */
+int32_t vkzg_ipa_verify_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* points, const vkzg_g1_affine* commitments,
+                              uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst,
+                              const vkzg_g1_affine* L, const vkzg_g1_affine* R, const vkzg_fr* tip, const vkzg_fr* y,
+                              int32_t* ok);
+/* ---- I4: IPA::prove_commitment / verify_commitment_proof (ipa/mod.rs:199-265) ------------------------- */
+int32_t vkzg_ipa_prove_commitment_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, const vkzg_g1_affine* commitments,
+                                        uint64_t B, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip);
+
+/* ---- P1: VectorCommitmentMultiproof::prove_multiproof (multiproof.rs:99-176) -------------------------- */
+/* scheme: 0 = IPA (key has q), 1 = KZG.  f[m][N], C[m], z[m], y[m].
+ * IPA outputs D, L[log2 N], R[log2 N], tip, yout;  KZG outputs D, L[0] = proof point, yout.             */
+int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
+                              const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
+                              vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout);
+/* ---- P2: verify_multiproof (multiproof.rs:178-215), IPA scheme; *ok = 1/0.  (KZG verification is two
+ *      pairings, kzg/mod.rs:165-189, and stays on the host side of the shim.)                            */
+int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* C, const uint64_t* z,
+                                   const vkzg_fr* y, uint64_t m, const vkzg_g1_affine* D, const vkzg_g1_affine* L,
+                                   const vkzg_g1_affine* R, const vkzg_fr* tip, const vkzg_fr* yproof, int32_t* ok);
+
+/* ---- T1: Node::gen_commitment (verkle-tree/src/node.rs:212-277), level-synchronous -------------------- */
+/* One level of node commitments in sparse (CSR) form.  Node j of the level commits to the terms
+ * [row_ptr[j], row_ptr[j+1]) : term t places at slot slot[t] either the literal scalar lit[t] (child[t] < 0)
+ * or to_data_item(nodes[child[t]]), where `nodes` is the array of ALL node commitments computed so far
+ * (child ids are global; a node's children live in earlier levels).  d_out receives this level's n_nodes
+ * commitments (normally d_nodes + the number of nodes of the earlier levels).                              */
+int32_t vkzg_tree_level_dev(vkzg_ctx* ctx, uint32_t key_id, const uint32_t* d_row_ptr, uint64_t n_nodes,
+                            const uint16_t* d_slot, const int32_t* d_child, const vkzg_fr* d_lit, uint64_t n_terms,
+                            const vkzg_g1_affine* d_nodes, vkzg_g1_affine* d_out);
+/* whole tree from host arrays: levels leaves-first, the last level is the single root node.               */
+int32_t vkzg_tree_commit_levels(vkzg_ctx* ctx, uint32_t key_id, uint32_t n_levels, const uint64_t* nodes_per_level,
+                                const uint32_t* const* row_ptr, const uint16_t* const* slot, const int32_t* const* child,
+                                const vkzg_fr* const* lit, vkzg_g1_affine* root_out);
+
+/* ---- measurement helpers (tools/, bench.py) ------------------------------------------------------------ */
+/* enable != 0: bracket every launch of the dominant kernel (k_fixed_base_msm for window keys, k_msm_bucket for
+ * MSM keys) with a CUDA event pair on the context's stream; calling it again clears the record.            */
+int32_t vkzg_ctx_kernel_timing(vkzg_ctx* ctx, int32_t enable);
+/* synchronises, then returns the number of bracketed launches and the sum of their durations */
+int32_t vkzg_ctx_kernel_timing_read(vkzg_ctx* ctx, uint64_t* launches, double* total_ms);
+/* runs `iters` dependent Fq multiplications on each of n elements in place: the integer-pipe probe */
+int32_t vkzg_probe_fq_mul_dev(vkzg_ctx* ctx, vkzg_fq* d_x, const vkzg_fq* d_y, uint64_t n, uint32_t iters);
+/* independent 32x32+64 multiply-accumulate chains on every SM; returns MAC32 issued (kind: 0 = mad.wide.u32,
+ * 1 = mad.lo.u32, 2 = mad.wide + carry chain, 3 = fma.rn.f64) */
+int32_t vkzg_probe_imad_dev(vkzg_ctx* ctx, uint32_t kind, uint32_t blocks, uint32_t threads, uint32_t iters,
+                            uint64_t* macs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

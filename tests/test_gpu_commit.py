@@ -1,0 +1,144 @@
+"""M1 / D1 parity on the GPU: libvkzg (through the C ABI) against the CPU oracle, compared as canonical
+affine bytes (a canonical point has one encoding, so equality of the 64-byte buffers is bit-exactness of
+the compressed serialisation too)."""
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from verkle_kzg_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _bases(n, seed):
+    rng = np.random.default_rng(seed)
+    k0, k1 = orc.rand_fr(rng, 2)
+    return orc.points_walk(k0, k1, n)
+
+
+@pytest.fixture(scope="module")
+def key257(eng):
+    bases = _bases(257, 1)
+    key = eng.load_key(bases[:256], q=bases[256])
+    return bases, key
+
+
+def test_table_spot_checks(eng):
+    """window tables at small width so that every entry can be checked: commit of unit-ish scalars"""
+    bases = _bases(4, 7)
+    key = eng.load_key(bases, window_bits=8)
+    # scalars chosen to hit digit magnitudes 1, 127, 128 (negative), carries, and the top window
+    vals = [1, 127, 128, 129, 255, 256, 2 ** 64 - 1, orc.R_MOD - 1, orc.R_MOD - 2, (orc.R_MOD - 1) // 2, 0x8080808080808080, 0]
+    for v in vals:
+        s = orc.fr_to_buf([v, 0, 0, 0]).reshape(1, 4, 32)
+        got = eng.commit_batch(key, s)[0]
+        exp = orc.g1_mul(bases[0], orc.fr_to_buf([v])[0])
+        assert (got == exp).all(), hex(v)
+    key.free()
+
+
+@pytest.mark.parametrize("w", [1, 4, 31, 32, 129, 256])
+def test_commit_batch_matches_oracle(eng, key257, w):
+    bases, key = key257
+    rng = np.random.default_rng(100 + w)
+    B = 5
+    s = orc.rand_fr_buf(rng, B * w).reshape(B, w, 32)
+    got = eng.commit_batch(key, s)
+    exp = orc.commit_batch(bases[:256], s)
+    assert (got == exp).all()
+
+
+def test_commit_edge_scalars(eng, key257):
+    bases, key = key257
+    edge = [0, 1, 2, orc.R_MOD - 1, orc.R_MOD - 2, 2 ** 128 - 1, 2 ** 128, 2 ** 253, 0x7fff, 0x8000, 0x8001, 0xffff, 0x10000,
+            (1 << 240) - 1, int("8000" * 15, 16), int("7fff" * 15, 16)]
+    s = orc.fr_to_buf(edge + [0] * (256 - len(edge))).reshape(1, 256, 32)
+    zero = np.zeros((1, 256, 32), dtype=np.uint8)
+    both = np.concatenate([s, zero])
+    got = eng.commit_batch(key, both)
+    exp = orc.commit_batch(bases[:256], both)
+    assert (got == exp).all()
+    assert not got[1].any()  # commitment to the zero vector is the identity
+
+
+def test_commit_linearity_full_batch(eng, key257):
+    """size-independent property at a larger batch: commit(a) + commit(b) == commit(a + b)"""
+    bases, key = key257
+    rng = np.random.default_rng(5)
+    B = 512
+    a = orc.rand_fr_buf(rng, B * 256)
+    b = orc.rand_fr_buf(rng, B * 256)
+    ab = orc.field_op(0, "add", a, b)
+    ca = eng.commit_batch(key, a.reshape(B, 256, 32))
+    cb = eng.commit_batch(key, b.reshape(B, 256, 32))
+    cab = eng.commit_batch(key, ab.reshape(B, 256, 32))
+    for i in range(0, B, 37):
+        assert (orc.g1_add(ca[i], cb[i]) == cab[i]).all()
+    # a few rows against the oracle directly
+    exp = orc.commit_batch(bases[:256], a.reshape(B, 256, 32)[:3])
+    assert (ca[:3] == exp).all()
+
+
+def test_commit_width_out_of_range(eng, key257):
+    from verkle_kzg_b200 import VkzgError
+    _, key = key257
+    s = np.zeros((1, 257, 32), dtype=np.uint8)
+    with pytest.raises(VkzgError):
+        eng.commit_batch(key, s)
+
+
+def test_to_data_item(eng, key257):
+    bases, _ = key257
+    pts = np.concatenate([bases[:40], np.zeros((1, 64), dtype=np.uint8)])
+    assert (eng.to_data_item(pts) == orc.to_data_item(pts)).all()
+
+
+def test_g1_sum(eng, key257):
+    bases, _ = key257
+    acc = np.zeros(64, dtype=np.uint8)
+    for p in bases[:19]:
+        acc = orc.g1_add(acc, p)
+    assert (eng.g1_sum(bases[:19]) == acc).all()
+    # P + (-P) + inf
+    trio = np.stack([bases[0], orc.g1_neg(bases[0]), np.zeros(64, dtype=np.uint8)])
+    assert not eng.g1_sum(trio).any()
+    # doubling inside the sum
+    assert (eng.g1_sum(np.stack([bases[3], bases[3]])) == orc.g1_add(bases[3], bases[3])).all()
+
+
+@pytest.mark.parametrize("n,c", [(1, 0), (5, 0), (1000, 0), (1 << 14, 0), (1 << 16, 0), (3000, 9)])
+def test_msm_matches_oracle(eng, n, c):
+    bases = _bases(n, 11 + n)
+    key = eng.load_key(bases, kind=2, window_bits=c)
+    rng = np.random.default_rng(n)
+    s = orc.rand_fr_buf(rng, n)
+    got = eng.msm(key, s)
+    exp = orc.msm(bases, s, mode="pippenger")
+    assert (got == exp).all()
+    if n <= 1000:
+        assert (got == orc.msm(bases, s, mode="naive")).all()
+    # zip truncation (quirk Q1): fewer scalars than bases
+    if n >= 5:
+        got2 = eng.msm(key, s[: n // 2])
+        assert (got2 == orc.msm(bases[: n // 2], s[: n // 2], mode="pippenger")).all()
+    key.free()
+
+
+def test_msm_degenerate_scalars(eng):
+    n = 4096
+    bases = _bases(n, 99)
+    key = eng.load_key(bases, kind=2)
+    same = np.tile(orc.fr_to_buf([0x1234567])[0], (n, 1))
+    assert (eng.msm(key, same) == orc.msm(bases, same, mode="pippenger")).all()
+    zero = np.zeros((n, 32), dtype=np.uint8)
+    assert not eng.msm(key, zero).any()
+    minus1 = np.tile(orc.fr_to_buf([orc.R_MOD - 1])[0], (n, 1))
+    assert (eng.msm(key, minus1) == orc.msm(bases, minus1, mode="pippenger")).all()
+    key.free()

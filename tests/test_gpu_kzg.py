@@ -1,0 +1,116 @@
+"""E1 / K1 / K2 / K3 parity on the GPU (kzg/mod.rs:278-297 restated + oracle byte equality)."""
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+TAU = 100  # kzg_point_generator.rs:20-26
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from verkle_kzg_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _key(eng, n, wb):
+    srs = orc.kzg_setup(n, TAU)
+    return srs, eng.load_key(srs, window_bits=wb)
+
+
+@pytest.mark.parametrize("N,length,domain,wb", [(16, 8, 16, 8), (16, 8, 0, 8), (16, 16, 0, 8), (32, 20, 32, 8), (32, 20, 0, 8),
+                                                 (256, 256, 0, 0)])
+def test_quotient_evaluate_open_match_oracle(eng, N, length, domain, wb):
+    """the reference's own test shape (DATA_SIZE 8 over the key's domain of 16, kzg/mod.rs:266-274), from_vec's own
+    domain, its bench shape (20 in 32) and width 256"""
+    srs, key = _key(eng, N, wb)
+    rng = np.random.default_rng(N * 1000 + length + domain)
+    want = domain if domain else length
+    dn = 1
+    while dn < want:
+        dn <<= 1
+    pts = list(range(0, min(length, 6))) + [length - 1]
+    if dn > length:
+        pts += [length, dn - 1]          # stored range exceeded but inside the data domain -> y = 0
+    if dn < N:
+        pts += [dn + 1, N - 1]           # beyond the data domain, below the key size
+    pts += [N + 1, 2 * N, orc.R_MOD - 2] + orc.rand_fr(rng, 2)  # (r - 1 = w^(n/2) is a root of unity: the reference divides by zero)
+    pts = [p for p in pts if not (p <= N and p >= dn)]  # the reference panics there (checked in the next test)
+    B = len(pts)
+    f = orc.rand_fr_buf(rng, B * length).reshape(B, length, 32)
+    zb = orc.fr_to_buf(pts)
+    ys = eng.evaluate_batch(key, f, zb, domain_n=domain)
+    q, y2 = eng.quotient_batch(key, f, zb, domain_n=domain)
+    proof, y3 = eng.kzg_open_batch(key, f, zb, domain_n=domain)
+    C = eng.commit_batch(key, f)
+    for i, p in enumerate(pts):
+        ey = orc.evaluate(N, f[i], want, zb[i])
+        assert (ys[i] == ey).all() and (y2[i] == ey).all() and (y3[i] == ey).all(), p
+        if p <= N:
+            eq = orc.divide_by_vanishing(N, f[i], want, p)
+        else:
+            eq = orc.divide_by_vanishing_outside(N, f[i], want, zb[i])
+        assert (q[i] == eq).all(), p
+        # proof = <SRS, q> (kzg/mod.rs:148-149)
+        assert (proof[i] == orc.msm(srs, eq)).all(), p
+        if dn == N:
+            epf, ey2, ok = orc.kzg_prove(srs, f[i], zb[i])  # the oracle's prove_point uses the key's domain
+            assert ok and (proof[i] == epf).all() and (y3[i] == ey2).all(), p
+            # pairing-free check with the known tau:  [tau - z] pi == C - [y] G   (oracle, kzg/mod.rs:165-189)
+            assert orc.kzg_verify_tau(srs, TAU, C[i], zb[i], proof[i], y3[i]), p
+    key.free()
+
+
+def test_point_equal_to_key_size_is_fenced(eng):
+    """quirk Q2: point == size takes the in-domain branch and indexes out of bounds in the reference"""
+    from verkle_kzg_b200 import VkzgError
+    N = 16
+    srs, key = _key(eng, N, 8)
+    f = orc.rand_fr_buf(np.random.default_rng(3), N).reshape(1, N, 32)
+    with pytest.raises(VkzgError) as ei:
+        eng.kzg_open_batch(key, f, orc.fr_to_buf([N]))
+    assert ei.value.status == -3
+    _, _, ok = orc.kzg_prove(srs, f[0], orc.fr_to_buf([N])[0])
+    assert not ok
+    key.free()
+
+
+def test_trait_surface_kzg(eng):
+    from verkle_kzg_b200.vector_commit import KZG, LagrangeBasis, OutOfDomain, fr_from_int
+    N = 16
+    srs = orc.kzg_setup(N, TAU)
+    key = KZG.setup(eng, srs, window_bits=8)
+    rng = np.random.default_rng(9)
+    data = LagrangeBasis.from_vec_and_domain(orc.rand_fr_buf(rng, 8), N)  # kzg/mod.rs:272
+    C = KZG.commit(key, data)
+    assert (C == orc.msm(srs, data.evaluations)).all()
+    for idx in (0, 3, 7, 17):
+        pf = KZG.prove(key, C, idx, data)
+        epf, ey, ok = orc.kzg_prove(srs, data.evaluations, orc.fr_to_buf([idx])[0])
+        assert ok and (pf["proof"] == epf).all() and (pf["y"] == ey).all()
+    with pytest.raises(OutOfDomain):
+        KZG.prove(key, C, 16, LagrangeBasis.from_vec(orc.rand_fr_buf(rng, 16)))
+    with pytest.raises(NotImplementedError):
+        KZG.verify(key, C, 0, pf)
+    key.free()
+
+
+def test_open_batch_property_full_width(eng):
+    """size-independent property on a larger batch: q(X) (X - z) == f(X) - y at X = tau, checked on the scalar side:
+    [q(tau)] G == proof  and  q(tau) (tau - z) == f(tau) - y, with f(tau) from the commitment side."""
+    N = 256
+    srs, key = _key(eng, N, 0)
+    rng = np.random.default_rng(12)
+    B = 200
+    f = orc.rand_fr_buf(rng, B * N).reshape(B, N, 32)
+    pts = [int(rng.integers(0, N)) for _ in range(B - 20)] + orc.rand_fr(rng, 20)
+    zb = orc.fr_to_buf(pts)
+    proof, y = eng.kzg_open_batch(key, f, zb)
+    C = eng.commit_batch(key, f)
+    for i in range(0, B, 9):
+        assert orc.kzg_verify_tau(srs, TAU, C[i], zb[i], proof[i], y[i])
+    key.free()

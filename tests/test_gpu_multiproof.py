@@ -1,0 +1,119 @@
+"""P1 / P2 parity on the GPU: multiproof.rs:261-357 restated (prove, verify, tamper) + oracle byte equality."""
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from verkle_kzg_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _queries(eng, key, rng, N, m, zs=None):
+    f = orc.rand_fr_buf(rng, m * N).reshape(m, N, 32)
+    C = eng.commit_batch(key, f)
+    z = np.array(zs if zs is not None else rng.integers(0, N, m), dtype=np.uint64)
+    y = np.stack([f[i, int(z[i])] for i in range(m)])
+    return f, C, z, y
+
+
+@pytest.mark.parametrize("N,m,wb", [(32, 20, 8), (32, 1, 8), (256, 64, 0)])
+def test_ipa_multiproof(eng, N, m, wb):
+    rng = np.random.default_rng(500 + N + m)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, N + 1)
+    key = eng.load_key(bases[:N], q=bases[N], window_bits=wb)
+    f, C, z, y = _queries(eng, key, rng, N, m)
+    got = eng.multiproof_prove(key, "ipa", f, C, z, y)
+    exp = orc.multiproof_prove("ipa", bases, N, f, C, z, y)
+    for k in ("D", "L", "R", "tip", "y"):
+        assert (got[k] == exp[k]).all(), k
+    assert orc.multiproof_verify("ipa", bases, N, C, z, y, got)
+    assert eng.multiproof_verify_ipa(key, C, z, y, got)
+    # tamper d and y (multiproof.rs:296-307)
+    bad = dict(got)
+    bad["D"] = bases[0]
+    assert not eng.multiproof_verify_ipa(key, C, z, y, bad)
+    y2 = y.copy()
+    y2[0] = orc.field_op(0, "add", y[0], orc.fr_to_buf([1])[0])[0]
+    assert not eng.multiproof_verify_ipa(key, C, z, y2, got)
+    key.free()
+
+
+def test_ipa_multiproof_skewed_groups(eng):
+    """all queries at one z (a single long group -> several segments), duplicates of one commitment, and z = N - 1"""
+    N, m = 32, 100
+    rng = np.random.default_rng(77)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, N + 1)
+    key = eng.load_key(bases[:N], q=bases[N], window_bits=8)
+    f, C, z, y = _queries(eng, key, rng, N, m, zs=[5] * 70 + [N - 1] * 30)
+    f[1] = f[0]
+    C[1] = C[0]
+    y[1] = y[0]
+    got = eng.multiproof_prove(key, "ipa", f, C, z, y)
+    exp = orc.multiproof_prove("ipa", bases, N, f, C, z, y)
+    for k in ("D", "L", "R", "tip", "y"):
+        assert (got[k] == exp[k]).all(), k
+    assert eng.multiproof_verify_ipa(key, C, z, y, got)
+    key.free()
+
+
+def test_kzg_multiproof(eng):
+    N, m = 32, 20
+    rng = np.random.default_rng(78)
+    srs = orc.kzg_setup(N, 100)
+    key = eng.load_key(srs, window_bits=8)
+    f, C, z, y = _queries(eng, key, rng, N, m)
+    got = eng.multiproof_prove(key, "kzg", f, C, z, y)
+    exp = orc.multiproof_prove("kzg", srs, N, f, C, z, y)
+    assert (got["D"] == exp["D"]).all() and (got["L"][0] == exp["L"][0]).all() and (got["y"] == exp["y"]).all()
+    assert orc.multiproof_verify("kzg", srs, N, C, z, y, got, tau=100)
+    key.free()
+
+
+def test_multiproof_rejects_out_of_range_z(eng):
+    from verkle_kzg_b200 import VkzgError
+    N = 32
+    rng = np.random.default_rng(79)
+    srs = orc.kzg_setup(N, 100)
+    key = eng.load_key(srs, window_bits=8)
+    f, C, z, y = _queries(eng, key, rng, N, 3)
+    z[1] = N
+    with pytest.raises(VkzgError):
+        eng.multiproof_prove(key, "kzg", f, C, z, y)
+    key.free()
+
+
+def test_trait_surface_ipa(eng):
+    from verkle_kzg_b200.vector_commit import IPA, LagrangeBasis
+    N = 32
+    rng = np.random.default_rng(80)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, N + 1)
+    key = IPA.setup(eng, bases[:N], q=bases[N], window_bits=8)
+    data = LagrangeBasis.from_vec(orc.rand_fr_buf(rng, N))
+    C = IPA.commit(key, data)
+    idx = 7
+    pf = IPA.prove(key, C, idx, data)
+    assert IPA.verify(key, C, idx, pf)
+    out = IPA.prove(key, C, 2 * N, data)            # outside the domain (ipa/mod.rs:413-416)
+    assert IPA.verify(key, C, 2 * N, out)
+    assert not IPA.verify(key, C, idx, out)
+    cp = IPA.prove_commitment(key, C, data)
+    assert orc.ipa_verify_commitment(bases, N, C, cp["l"], cp["r"], cp["tip"])
+    queries = []
+    for i in range(20):
+        d = LagrangeBasis.from_vec(orc.rand_fr_buf(rng, N))
+        z = int(rng.integers(0, N))
+        queries.append((d, IPA.commit(key, d), z, d.evaluations[z]))
+    mp = IPA.prove_multiproof(key, queries)
+    vq = [(q[1], q[2], q[3]) for q in queries]
+    assert IPA.verify_multiproof(key, vq, mp)
+    key.free()

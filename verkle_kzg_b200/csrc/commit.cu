@@ -1,0 +1,200 @@
+// M1 for width-N vectors: `jobs` independent fixed-base MSMs, one warp each.
+//
+// utils::inner_product (utils.rs:16-19) multiplies every base by its scalar with a 254-bit
+// double-and-add.  The bases of a key never change, so here every term is W table look-ups instead:
+// the scalar is recoded into W signed c-bit digits d_w and  s * P = sum_w T[P][w][|d_w|] * sign(d_w).
+// A warp turns a chunk of 128 scalars into a compact list of (table index, sign) entries in shared
+// memory, its lanes then walk that list 32 entries at a time — perfectly balanced whatever the number
+// of terms or zero digits — each lane adding into its own XYZZ accumulator with a 64-byte vectorised
+// gather per addition (the next entry's point is in flight while the current one is added).  The 32
+// accumulators are summed with a shuffle tree.
+#include "vk_common.cuh"
+
+namespace vk {
+
+__device__ __forceinline__ affine_t load_affine_ro(const affine_t* p) {
+    affine_t a;
+    a.x = fp_load_ro(&p->x);
+    a.y = fp_load_ro(&p->y);
+    return a;
+}
+
+__device__ __forceinline__ xyzz_t shfl_down_xyzz(const xyzz_t& v, int off) {
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], off);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], off);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], off);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], off);
+    }
+    return r;
+}
+
+// Recode one canonical scalar into signed c-bit digits and append the non-zero ones to `list`.
+__device__ __forceinline__ void emit_entries(const fp_t& k, uint32_t row_base /* base * W */, uint32_t c, uint32_t W,
+                                             uint32_t* list, uint32_t* cnt) {
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t v = scalar_bits(k.l, w * c, c) + carry;
+        uint32_t neg = v >= half && w + 1 < W ? 1u : 0u;  // the top window never needs to borrow (k < r < 2^254)
+        uint32_t mag = neg ? (1u << c) - v : v;
+        carry = neg;
+        if (mag) {
+            uint32_t pos = atomicAdd(cnt, 1u);
+            list[pos] = (((row_base + w) << (c - 1)) + (mag - 1)) | (neg << 31);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    k_fixed_base_msm(const affine_t* __restrict__ table, uint32_t c, uint32_t W, const fp_t* __restrict__ scalars, uint32_t T,
+                     uint64_t jobs, uint32_t ipa_m, uint32_t q_row, const uint32_t* __restrict__ row_ptr,
+                     const uint16_t* __restrict__ slot, xyzz_t* __restrict__ out) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t list_cap = CHUNK_TERMS * W;
+    uint32_t* list = smem + warp * (list_cap + 32);
+    uint32_t* cnt = list + list_cap;
+    uint64_t job = (uint64_t)blockIdx.x * WARPS_PER_CTA + warp;
+    if (job >= jobs) return;
+    // dense: job j owns scalars[j*T .. (j+1)*T), term t uses base t.  CSR (row_ptr != nullptr, verkle nodes):
+    // job j owns terms [row_ptr[j], row_ptr[j+1]) and term t uses base slot[t].
+    const fp_t* sc = scalars + job * T;
+    const uint16_t* sl = nullptr;
+    if (row_ptr) {
+        uint32_t t0 = row_ptr[job];
+        T = row_ptr[job + 1] - t0;
+        sc = scalars + t0;
+        sl = slot + t0;
+    }
+    // ipa_m != 0: job 2p is the L cross term of proof p, job 2p+1 the R cross term of an IPA round whose
+    // half length is ipa_m (see ipa.cu): term j < T-1 uses base (j / m) * 2m + (L ? m : 0) + j % m and the
+    // last term the base q_row (when q_row != 0xffffffff)
+    const uint32_t side_off = (job & 1) ? 0u : ipa_m;
+
+    xyzz_t acc = xyzz_inf();
+    for (uint32_t chunk = 0; chunk < T; chunk += CHUNK_TERMS) {
+        if (lane == 0) *cnt = 0;
+        __syncwarp();
+        for (uint32_t j = lane; j < CHUNK_TERMS; j += 32) {
+            uint32_t term = chunk + j;
+            if (term < T) {
+                fp_t k = fp_from_mont<S>(fp_load_ro(sc + term));
+                uint32_t base = sl ? (uint32_t)sl[term] : term;
+                if (ipa_m) base = (term == T - 1 && q_row != 0xffffffffu) ? q_row : (term / ipa_m) * 2 * ipa_m + side_off + term % ipa_m;
+                emit_entries(k, base * W, c, W, list, cnt);
+            }
+        }
+        __syncwarp();
+        const uint32_t n = *cnt;
+        uint32_t t = lane;
+        uint32_t e = 0;
+        affine_t cur;
+        if (t < n) {
+            e = list[t];
+            cur = load_affine_ro(table + (e & 0x7fffffffu));
+        }
+        while (t < n) {
+            uint32_t tn = t + 32, en = 0;
+            affine_t nxt;
+            if (tn < n) {
+                en = list[tn];
+                nxt = load_affine_ro(table + (en & 0x7fffffffu));
+            }
+            if (e >> 31) cur.y = fp_neg<Q>(cur.y);
+            xyzz_madd(acc, cur);
+            cur = nxt;
+            e = en;
+            t = tn;
+        }
+        __syncwarp();
+    }
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, off);
+        if (lane < (uint32_t)off) acc = xyzz_add(acc, o);
+    }
+    if (lane == 0) {
+        fp_store(&out[job].x, acc.x);
+        fp_store(&out[job].y, acc.y);
+        fp_store(&out[job].zz, acc.zz);
+        fp_store(&out[job].zzz, acc.zzz);
+    }
+}
+
+int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
+                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out) {
+    if (jobs == 0) return VKZG_OK;
+    size_t smem = (size_t)WARPS_PER_CTA * (CHUNK_TERMS * k.W + 32) * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    uint64_t blocks = (jobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (blocks > 0x7fffffffull) return VKZG_ERR_RANGE;
+    KernelTimer timer(ctx);
+    k_fixed_base_msm<<<(uint32_t)blocks, WARPS_PER_CTA * 32, smem, ctx->stream>>>(k.table, k.c, k.W, d_scalars, T, jobs, ipa_m,
+                                                                                  q_row, d_row_ptr, d_slot, d_out);
+    return launch_check(ctx);
+}
+
+int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
+                       uint32_t q_row, xyzz_t* d_out) {
+    return fixed_base_msm_csr(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, d_out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// sum of n affine points -> one affine point (combine step for sharded MSMs); single CTA tree.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_g1_sum(const affine_t* __restrict__ pts, uint64_t n, xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[256];
+    xyzz_t acc = xyzz_inf();
+    for (uint64_t i = threadIdx.x; i < n; i += 256) xyzz_madd(acc, pts[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+int32_t g1_sum(vkzg_ctx* ctx, const affine_t* d_points, uint64_t n, affine_t* d_out) {
+    DevBuf<xyzz_t> acc;
+    VK_TRY(acc.alloc(ctx, 1));
+    k_g1_sum<<<1, 256, 0, ctx->stream>>>(d_points, n, acc);
+    VK_TRY(launch_check(ctx));
+    return normalize_points(ctx, acc, 1, d_out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// D1: VCCommitment::to_data_item (vector-commit/src/lib.rs:56-67): identity -> 0, else the 32 compressed
+// bytes (flag bits included, quirk Q7) reduced mod r.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_to_data_item(const affine_t* __restrict__ pts, uint64_t n, fp_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p;
+    p.x = fp_load(&pts[i].x);
+    p.y = fp_load(&pts[i].y);
+    fp_t r = fp_zero<S>();
+    if (!affine_is_inf(p)) {
+        fp_t v, r2;
+        affine_compress(p, v.l);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r2.l[k] = S::r2(k);
+        r = fp_mul<S>(r2, v);
+    }
+    fp_store(out + i, r);
+}
+
+int32_t to_data_item(vkzg_ctx* ctx, const affine_t* d_points, uint64_t n, fp_t* d_out) {
+    if (n == 0) return VKZG_OK;
+    k_to_data_item<<<ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(d_points, n, d_out);
+    return launch_check(ctx);
+}
+
+}  // namespace vk

@@ -194,9 +194,9 @@ __host__ __device__ inline fp_t fr_from_le32_mod_order(const uint8_t b[32]) {
     return fp_mul_ni<S>(r2, v);  // first operand < r, second any 256-bit value
 }
 
-// Transcript state: at most TR_MAX bytes (prefix <= 128, the IPA opening adds <= 121 before the first
+// Transcript state: at most TR_MAX bytes (prefix <= 160, the IPA opening adds <= 121 before the first
 // clearing digest, every later round holds 100).
-static const uint32_t TR_MAX = 256;
+static const uint32_t TR_MAX = 320;
 static const uint32_t TR_DST_MAX = 16;
 
 struct transcript_t {

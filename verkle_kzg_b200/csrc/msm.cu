@@ -1,0 +1,230 @@
+// M1 at large n (BASELINE config 4): one Pippenger MSM over a VKZG_KEY_MSM key.
+//
+// The key holds T[w][i] = 2^(c w) * P_i, so every signed c-bit digit of every scalar lands in ONE shared
+// set of 2^(c-1) buckets (no per-window bucket sets, no final doubling chain):
+//     sum_i s_i P_i = sum_b (b + 1) * B_b ,   B_b = sum over digits of magnitude b + 1 of +-T[w][i].
+//   1. k_msm_count    one thread per scalar: Montgomery -> canonical, signed recode, histogram of buckets
+//   2. k_scan         exclusive prefix sum of the bucket sizes
+//   3. k_msm_scatter  counting-sort scatter of (table index, sign) entries into bucket order
+//   4. k_msm_bucket   P lanes per bucket (P adjacent lanes, interleaved slices -> equal work), 64-byte
+//                     vectorised gathers one entry ahead of the mixed addition, shuffle-tree fold of the
+//                     P partial sums
+//   5. k_msm_reduce   weighted bucket sum: per-thread running sums over 8 buckets, a small scalar multiple
+//                     for the segment offset, shared-memory tree per CTA
+//   6. k_xyzz_sum     CTA results -> one point, then the common normalisation kernel
+// The order in which a bucket's points are added is not deterministic (atomics), the result is: it leaves
+// the device in canonical affine form.
+#include "vk_common.cuh"
+
+namespace vk {
+
+__device__ __forceinline__ affine_t load_affine_ro2(const affine_t* p) {
+    affine_t a;
+    a.x = fp_load_ro(&p->x);
+    a.y = fp_load_ro(&p->y);
+    return a;
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_msm_digits(const fp_t* __restrict__ scalars, uint64_t n, uint32_t c, uint32_t W,
+                                                    uint32_t key_n, uint64_t first, uint32_t* __restrict__ hist_or_cursor,
+                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_t k = fp_from_mont<S>(fp_load_ro(scalars + i));
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t v = scalar_bits(k.l, w * c, c) + carry;
+        uint32_t neg = v >= half && w + 1 < W ? 1u : 0u;
+        uint32_t mag = neg ? (1u << c) - v : v;
+        carry = neg;
+        if (mag) {
+            uint32_t b = mag - 1;
+            uint32_t pos = atomicAdd(hist_or_cursor + b, 1u);
+            if (SCATTER) entries[offsets[b] + pos] = (uint32_t)((uint64_t)w * key_n + first + i) | (neg << 31);
+        }
+    }
+}
+
+// single-CTA exclusive scan of `n` counts (n <= 2^20), also zeroes the counts for their second life as cursors
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t sh[1024];
+    uint32_t per = (n + 1023) / 1024;
+    uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += counts[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = sh[threadIdx.x] - s;
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t cnt = counts[i];
+        offsets[i] = run;
+        counts[i] = 0;
+        run += cnt;
+    }
+    if (threadIdx.x == 1023) offsets[n] = sh[1023];
+}
+
+__device__ __forceinline__ xyzz_t shfl_xor_xyzz(const xyzz_t& v, int mask) {
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], mask);
+        r.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], mask);
+        r.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], mask);
+        r.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], mask);
+    }
+    return r;
+}
+
+// P (power of two <= 32) adjacent lanes per bucket
+__global__ void __launch_bounds__(128) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
+                                                    const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P,
+                                                    xyzz_t* __restrict__ buckets) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = (uint32_t)(t / P), p = (uint32_t)(t % P);
+    bool live = b < nb;
+    uint32_t lo = 0, hi = 0;
+    if (live) {
+        lo = offsets[b];
+        hi = offsets[b + 1];
+    }
+    xyzz_t acc = xyzz_inf();
+    uint32_t i = lo + p, e = 0;
+    affine_t cur;
+    if (i < hi) {
+        e = __ldg(entries + i);
+        cur = load_affine_ro2(table + (e & 0x7fffffffu));
+    }
+    while (i < hi) {
+        uint32_t in = i + P, en = 0;
+        affine_t nxt;
+        if (in < hi) {
+            en = __ldg(entries + in);
+            nxt = load_affine_ro2(table + (en & 0x7fffffffu));
+        }
+        if (e >> 31) cur.y = fp_neg<Q>(cur.y);
+        xyzz_madd(acc, cur);
+        cur = nxt;
+        e = en;
+        i = in;
+    }
+#pragma unroll 1
+    for (uint32_t m = 1; m < P; m <<= 1) {
+        xyzz_t o = shfl_xor_xyzz(acc, (int)m);
+        acc = xyzz_add(acc, o);
+    }
+    if (live && p == 0) {
+        fp_store(&buckets[b].x, acc.x);
+        fp_store(&buckets[b].y, acc.y);
+        fp_store(&buckets[b].zz, acc.zz);
+        fp_store(&buckets[b].zzz, acc.zzz);
+    }
+}
+
+__device__ __noinline__ xyzz_t xyzz_mul_small(const xyzz_t p, uint32_t k) {
+    xyzz_t acc = xyzz_inf();
+    if (k == 0) return acc;
+    int top = 31 - __clz(k);
+    for (int b = top; b >= 0; --b) {
+        acc = xyzz_dbl_ni(acc);
+        if ((k >> b) & 1) acc = xyzz_add_ni(acc, p);
+    }
+    return acc;
+}
+
+static const int RED_SEG = 8;
+static const int RED_THREADS = 128;
+
+// sum_b (b + 1) B_b: thread = segment of RED_SEG buckets, CTA tree, one XYZZ per CTA
+__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(const xyzz_t* __restrict__ buckets, uint32_t nb, xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[RED_THREADS];
+    uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;
+    uint32_t lo = seg * RED_SEG;
+    xyzz_t run = xyzz_inf(), sum = xyzz_inf();
+    if (lo < nb) {
+        uint32_t hi = lo + RED_SEG < nb ? lo + RED_SEG : nb;
+#pragma unroll 1
+        for (uint32_t b = hi; b-- > lo;) {
+            xyzz_t B;
+            B.x = fp_load(&buckets[b].x);
+            B.y = fp_load(&buckets[b].y);
+            B.zz = fp_load(&buckets[b].zz);
+            B.zzz = fp_load(&buckets[b].zzz);
+            run = xyzz_add_ni(run, B);
+            sum = xyzz_add_ni(sum, run);
+        }
+        // weights inside the segment were 1..RED_SEG; the true ones are lo + 1 .. lo + RED_SEG
+        if (lo) sum = xyzz_add_ni(sum, xyzz_mul_small(run, lo));
+    }
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = RED_THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(256) k_xyzz_sum(const xyzz_t* __restrict__ pts, uint32_t n, xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[256];
+    xyzz_t acc = xyzz_inf();
+    for (uint32_t i = threadIdx.x; i < n; i += 256) acc = xyzz_add_ni(acc, pts[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out) {
+    const uint32_t nb = 1u << (k.c - 1);
+    DevBuf<uint32_t> counts, offsets, entries;
+    DevBuf<xyzz_t> buckets, partial;
+    VK_TRY(counts.alloc(ctx, nb));
+    VK_TRY(offsets.alloc(ctx, nb + 1));
+    VK_TRY(entries.alloc(ctx, (size_t)n * k.W));
+    VK_TRY(buckets.alloc(ctx, nb));
+    cudaStream_t s = ctx->stream;
+    VK_CUDA(cudaMemsetAsync(counts, 0, nb * sizeof(uint32_t), s));
+    uint32_t gb = ceil_div_u64(n, 256);
+    if (n) {
+        k_msm_digits<false><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, nullptr, nullptr);
+        VK_TRY(launch_check(ctx));
+    }
+    k_scan<<<1, 1024, 0, s>>>(counts, nb, offsets);
+    VK_TRY(launch_check(ctx));
+    if (n) {
+        k_msm_digits<true><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, offsets, entries);
+        VK_TRY(launch_check(ctx));
+    }
+    // lanes per bucket: aim at ~24 additions per lane
+    uint64_t avg = (uint64_t)n * k.W / nb;
+    uint32_t P = 1;
+    while (P < 32 && avg / (P * 2) >= 16) P *= 2;
+    uint64_t threads = (uint64_t)nb * P;
+    {
+        KernelTimer timer(ctx);
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries, nb, P, buckets);
+    }
+    VK_TRY(launch_check(ctx));
+    uint32_t segs = (nb + RED_SEG - 1) / RED_SEG;
+    uint32_t rblocks = (segs + RED_THREADS - 1) / RED_THREADS;
+    VK_TRY(partial.alloc(ctx, rblocks + 1));
+    k_msm_reduce<<<rblocks, RED_THREADS, 0, s>>>(buckets, nb, partial);
+    VK_TRY(launch_check(ctx));
+    k_xyzz_sum<<<1, 256, 0, s>>>(partial, rblocks, partial.p + rblocks);
+    VK_TRY(launch_check(ctx));
+    return normalize_points(ctx, partial.p + rblocks, 1, d_out);
+}
+
+}  // namespace vk

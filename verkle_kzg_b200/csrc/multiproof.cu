@@ -1,0 +1,390 @@
+// P1 / P2: VectorCommitmentMultiproof::prove_multiproof / verify_multiproof (multiproof.rs:99-215).
+//
+// The m x N input (m queries of width N) is read from HBM exactly once:
+//     total_z = sum_{q : z_q = z} r^q f_q                              (multiproof.rs:119-143)
+//     g = sum_z divide_by_vanishing(total_z, z),   D = commit(g)       (:130-151)
+//     h = sum_z total_z / (t - z)                                      (:158-166; integer z, quirk Q4 —
+//         the reference loops over all m scaled rows; grouping by z first is the same field element)
+//     E = commit(h);  proof = prove_point(E - D, t, h - g)             (:168-174)
+// The Fiat-Shamir state of the OUTER transcript (the m (C, z, y) triples -> r, then D -> t, then E) is
+// a strictly serial SHA-256 chain over ~75 m bytes of caller-supplied host data; it is hashed on the host
+// while the rows upload (a single GPU thread would need ~2.5 us per 64-byte block).  Everything that touches
+// the rows — powers of r, the segmented row sums, quotients, h, both commitments and the final opening
+// with its own round challenges — runs on the device.
+#include "vk_common.cuh"
+
+namespace vk {
+
+// ---- host side of the outer transcript (hash.cuh is host/device code) ----------------------------------
+struct HostTranscript {
+    std::vector<uint8_t> state;
+    uint8_t dst[TR_DST_MAX];
+    uint32_t dst_len;
+    explicit HostTranscript(const char* label) {
+        dst_len = (uint32_t)strlen(label);
+        memcpy(dst, label, dst_len);
+    }
+    void append_raw(const void* p, size_t n) {
+        const uint8_t* b = (const uint8_t*)p;
+        state.insert(state.end(), b, b + n);
+    }
+    void append_label(const char* l) { append_raw(l, strlen(l)); }
+    void append_point(const affine_t& p, const char* l) {
+        uint8_t b[32];
+        append_label(l);
+        affine_serialize(p, b);
+        append_raw(b, 32);
+    }
+    void append_fr(const fp_t& x, const char* l) {
+        uint8_t b[32];
+        append_label(l);
+        fr_serialize(x, b);
+        append_raw(b, 32);
+    }
+    void append_u64(uint64_t v, const char* l) {  // usize -> u64 little-endian (quirk Q5)
+        uint8_t b[8];
+        for (int i = 0; i < 8; ++i) b[i] = (uint8_t)(v >> (8 * i));
+        append_label(l);
+        append_raw(b, 8);
+    }
+    fp_t digest(const char* l) {
+        append_label(l);
+        fp_t res = hash_to_fr(state.data(), (uint32_t)state.size(), dst, dst_len);
+        uint8_t b[32];
+        fr_serialize(res, b);
+        state.assign(b, b + 32);
+        append_label(l);
+        return res;
+    }
+};
+
+// ---- device kernels --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_powers(fp_t r, uint64_t m, fp_t* __restrict__ out) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    fp_t acc = fp_one<S>();
+    for (int b = 63 - __clzll(q | 1); b >= 0; --b) {
+        acc = fp_mul_ni<S>(acc, acc);
+        if ((q >> b) & 1) acc = fp_mul_ni<S>(acc, r);
+    }
+    fp_store(out + q, acc);
+}
+
+// partial[s][i] = sum over the queries of segment s of r^q f_q[i].   grid: (N / 128, segments)
+__global__ void __launch_bounds__(128) k_mp_segments(const fp_t* __restrict__ f, const fp_t* __restrict__ rpow,
+                                                     const uint32_t* __restrict__ seg_ptr, const uint32_t* __restrict__ order,
+                                                     uint32_t N, fp_t* __restrict__ partial) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = blockIdx.y;
+    if (i >= N) return;
+    fp_t acc = fp_zero<S>();
+    for (uint32_t k = seg_ptr[s]; k < seg_ptr[s + 1]; ++k) {
+        uint32_t q = order[k];
+        acc = fp_add<S>(acc, fp_mul<S>(fp_load_ro(rpow + q), fp_load_ro(f + (size_t)q * N + i)));
+    }
+    fp_store(partial + (size_t)s * N + i, acc);
+}
+
+// total[g][i] = sum of the partial rows of group g.   grid: (N / 128, groups)
+__global__ void __launch_bounds__(128) k_mp_groups(const fp_t* __restrict__ partial, const uint32_t* __restrict__ grp_ptr, uint32_t N,
+                                                   fp_t* __restrict__ total) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t g = blockIdx.y;
+    if (i >= N) return;
+    fp_t acc = fp_zero<S>();
+    for (uint32_t s = grp_ptr[g]; s < grp_ptr[g + 1]; ++s) acc = fp_add<S>(acc, fp_load(partial + (size_t)s * N + i));
+    fp_store(total + (size_t)g * N + i, acc);
+}
+
+// g[i] = sum over groups of quotient rows
+__global__ void __launch_bounds__(128) k_mp_colsum(const fp_t* __restrict__ rows, uint32_t n_rows, uint32_t N, fp_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    fp_t acc = fp_zero<S>();
+    for (uint32_t g = 0; g < n_rows; ++g) acc = fp_add<S>(acc, fp_load(rows + (size_t)g * N + i));
+    fp_store(out + i, acc);
+}
+
+// inv[g] = 1 / (t - z_g)   (utils.rs:57-62 for the z that occur)
+__global__ void __launch_bounds__(64) k_mp_inv(fp_t t, const fp_t* __restrict__ zf, uint32_t n, fp_t* __restrict__ inv) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    fp_store(inv + g, fp_inv<S>(fp_sub<S>(t, fp_load(zf + g))));
+}
+
+// h[i] = sum_g inv[g] total[g][i];  hmg = h - g
+__global__ void __launch_bounds__(128) k_mp_h(const fp_t* __restrict__ total, const fp_t* __restrict__ inv, uint32_t n_groups,
+                                              uint32_t N, const fp_t* __restrict__ gvec, fp_t* __restrict__ h,
+                                              fp_t* __restrict__ hmg) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    fp_t acc = fp_zero<S>();
+    for (uint32_t g = 0; g < n_groups; ++g) acc = fp_add<S>(acc, fp_mul<S>(fp_load_ro(inv + g), fp_load(total + (size_t)g * N + i)));
+    fp_store(h + i, acc);
+    fp_store(hmg + i, fp_sub<S>(acc, fp_load(gvec + i)));
+}
+
+// out = a - b
+__global__ void k_point_sub(const affine_t* a, const affine_t* b, affine_t* out) {
+    xyzz_t acc = xyzz_from_affine(*a);
+    xyzz_madd(acc, affine_neg(*b));
+    *out = xyzz_to_affine(acc);
+}
+
+// variable-base scalar multiplications, thread per point (verify_multiproof's E, multiproof.rs:211)
+__global__ void __launch_bounds__(128) k_var_mul(const affine_t* __restrict__ pts, const fp_t* __restrict__ sc, uint64_t n,
+                                                 xyzz_t* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    affine_t P;
+    P.x = fp_load(&pts[t].x);
+    P.y = fp_load(&pts[t].y);
+    fp_t k = fp_from_mont<S>(fp_load(sc + t));
+    xyzz_t acc = xyzz_inf();
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; --bit) {
+        acc = xyzz_dbl_ni(acc);
+        uint32_t limb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i == (bit >> 5)) limb = k.l[i];
+        if ((limb >> (bit & 31)) & 1) xyzz_madd(acc, P);
+    }
+    out[t] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_xyzz_tree(const xyzz_t* __restrict__ pts, uint64_t n, xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[256];
+    xyzz_t acc = xyzz_inf();
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) acc = xyzz_add_ni(acc, pts[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+int32_t var_base_msm(vkzg_ctx* ctx, const affine_t* d_points, const fp_t* d_scalars, uint64_t n, affine_t* d_out) {
+    DevBuf<xyzz_t> prod, part;
+    VK_TRY(prod.alloc(ctx, n));
+    uint32_t blocks = n > 256 * 8 ? 64 : 1;
+    VK_TRY(part.alloc(ctx, blocks + 1));
+    if (n) {
+        k_var_mul<<<ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(d_points, d_scalars, n, prod);
+        VK_TRY(launch_check(ctx));
+    }
+    k_xyzz_tree<<<blocks, 256, 0, ctx->stream>>>(prod, n, part);
+    VK_TRY(launch_check(ctx));
+    if (blocks > 1) {
+        k_xyzz_tree<<<1, 256, 0, ctx->stream>>>(part, blocks, part.p + blocks);
+        VK_TRY(launch_check(ctx));
+        return normalize_points(ctx, part.p + blocks, 1, d_out);
+    }
+    return normalize_points(ctx, part, 1, d_out);
+}
+
+__global__ void __launch_bounds__(128) k_fr_mul(const fp_t* a, const fp_t* b, uint64_t n, fp_t* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_store(out + i, fp_mul<S>(fp_load(a + i), fp_load(b + i)));
+}
+static int32_t fr_mul_elementwise(vkzg_ctx* ctx, const fp_t* a, const fp_t* b, uint64_t n, fp_t* out) {
+    if (!n) return VKZG_OK;
+    k_fr_mul<<<ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(a, b, n, out);
+    return launch_check(ctx);
+}
+
+static const uint32_t MP_SEG = 32;  // queries per segment of the row sum
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" {
+
+int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
+                              const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
+                              vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
+    if (!m || !f || !C || !z || !y || !D || !L || !yout) return VKZG_ERR_ARG;
+    if (scheme != 0 && scheme != 1) return VKZG_ERR_ARG;
+    if (scheme == 0 && (!k->has_q || !R || !tip)) return VKZG_ERR_ARG;
+    const uint32_t N = k->n;
+    if (N & (N - 1)) return VKZG_ERR_UNSUPPORTED;
+    if (m >= (1ull << 31)) return VKZG_ERR_RANGE;
+    for (uint64_t q = 0; q < m; ++q)
+        if (z[q] >= N) return VKZG_ERR_RANGE;  // reference: vanishing_at(z) out of bounds
+    cudaStream_t s = ctx->stream;
+
+    // rows to the device first (asynchronous for pinned memory), so the host hash below overlaps the copy
+    DevBuf<fp_t> df;
+    VK_TRY(upload(ctx, df, f, m * N));
+
+    // outer transcript: (C, z, y) per query -> r          multiproof.rs:108-115
+    HostTranscript tr("multiproof");
+    tr.state.reserve(m * 75 + 64);
+    for (uint64_t q = 0; q < m; ++q) {
+        tr.append_point(((const affine_t*)C)[q], "C");
+        tr.append_u64(z[q], "z");
+        tr.append_fr(((const fp_t*)y)[q], "y");
+    }
+    fp_t r = tr.digest("r");
+
+    // group the queries by z, split every group into segments of <= MP_SEG queries
+    std::vector<uint32_t> cnt(N + 1, 0), order(m), grp_z, grp_ptr(1, 0), seg_ptr(1, 0);
+    for (uint64_t q = 0; q < m; ++q) cnt[z[q] + 1]++;
+    for (uint32_t i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
+    {
+        std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+        for (uint64_t q = 0; q < m; ++q) order[cur[z[q]]++] = (uint32_t)q;
+    }
+    for (uint32_t zz = 0; zz < N; ++zz) {
+        uint32_t lo = cnt[zz], hi = cnt[zz + 1];
+        if (lo == hi) continue;
+        grp_z.push_back(zz);
+        for (uint32_t a = lo; a < hi; a += MP_SEG) seg_ptr.push_back(std::min(hi, a + MP_SEG));
+        grp_ptr.push_back((uint32_t)seg_ptr.size() - 1);
+    }
+    const uint32_t n_groups = (uint32_t)grp_z.size(), n_segs = (uint32_t)seg_ptr.size() - 1;
+    std::vector<fp_t> zf(n_groups);
+    for (uint32_t g = 0; g < n_groups; ++g) zf[g] = fp_from_u32<S>(grp_z[g]);
+
+    DevBuf<uint32_t> d_order, d_seg_ptr, d_grp_ptr;
+    DevBuf<fp_t> d_zf, rpow, partial, total, quo, gvec, inv, h, hmg, dy;
+    DevBuf<affine_t> DE, Cdiff, dL, dR;
+    DevBuf<xyzz_t> acc;
+    VK_TRY(upload(ctx, d_order, order.data(), m));
+    VK_TRY(upload(ctx, d_seg_ptr, seg_ptr.data(), seg_ptr.size()));
+    VK_TRY(upload(ctx, d_grp_ptr, grp_ptr.data(), grp_ptr.size()));
+    VK_TRY(upload(ctx, d_zf, zf.data(), n_groups));
+    VK_TRY(rpow.alloc(ctx, m));
+    VK_TRY(partial.alloc(ctx, (size_t)n_segs * N));
+    VK_TRY(total.alloc(ctx, (size_t)n_groups * N));
+    VK_TRY(quo.alloc(ctx, (size_t)n_groups * N));
+    VK_TRY(gvec.alloc(ctx, N));
+    VK_TRY(inv.alloc(ctx, n_groups));
+    VK_TRY(h.alloc(ctx, N));
+    VK_TRY(hmg.alloc(ctx, N));
+    VK_TRY(dy.alloc(ctx, n_groups > 1 ? n_groups : 1));
+    VK_TRY(DE.alloc(ctx, 2));
+    VK_TRY(Cdiff.alloc(ctx, 1));
+    VK_TRY(acc.alloc(ctx, 1));
+
+    k_powers<<<ceil_div_u64(m, 128), 128, 0, s>>>(r, m, rpow);
+    VK_TRY(launch_check(ctx));
+    dim3 gs((N + 127) / 128, n_segs), gg((N + 127) / 128, n_groups);
+    k_mp_segments<<<gs, 128, 0, s>>>(df, rpow, d_seg_ptr, d_order, N, partial);
+    VK_TRY(launch_check(ctx));
+    k_mp_groups<<<gg, 128, 0, s>>>(partial, d_grp_ptr, N, total);
+    VK_TRY(launch_check(ctx));
+    // quotients of the group totals at their (in-domain) points, summed into g
+    VK_TRY(poly_batch(ctx, *k, total, N, 0, d_zf, n_groups, quo, dy, false));
+    k_mp_colsum<<<(N + 127) / 128, 128, 0, s>>>(quo, n_groups, N, gvec);
+    VK_TRY(launch_check(ctx));
+    // D = commit(g)
+    VK_TRY(fixed_base_msm(ctx, *k, gvec, N, 1, 0, 0xffffffffu, acc));
+    VK_TRY(normalize_points(ctx, acc, 1, DE.p));
+    affine_t hD, hE;
+    VK_TRY(download(ctx, &hD, DE.p, 1));
+    VK_TRY(stream_sync(ctx));
+    tr.append_point(hD, "D");
+    fp_t t = tr.digest("t");  // multiproof.rs:152-155
+    k_mp_inv<<<ceil_div_u64(n_groups, 64), 64, 0, s>>>(t, d_zf, n_groups, inv);
+    VK_TRY(launch_check(ctx));
+    k_mp_h<<<(N + 127) / 128, 128, 0, s>>>(total, inv, n_groups, N, gvec, h, hmg);
+    VK_TRY(launch_check(ctx));
+    VK_TRY(fixed_base_msm(ctx, *k, h, N, 1, 0, 0xffffffffu, acc));
+    VK_TRY(normalize_points(ctx, acc, 1, DE.p + 1));
+    k_point_sub<<<1, 1, 0, s>>>(DE.p + 1, DE.p, Cdiff);
+    VK_TRY(launch_check(ctx));
+    VK_TRY(download(ctx, &hE, DE.p + 1, 1));
+    VK_TRY(stream_sync(ctx));
+    tr.append_point(hE, "E");  // multiproof.rs:168-169
+
+    // final opening of h - g at t against E - D, continuing the transcript (multiproof.rs:171-174)
+    DevBuf<fp_t> dt, dtip, dyo;
+    VK_TRY(upload(ctx, dt, &t, 1));
+    VK_TRY(dyo.alloc(ctx, 1));
+    memcpy(D, &hD, sizeof(hD));
+    if (scheme == 0) {
+        const uint32_t rounds = k->log2n;
+        VK_TRY(dL.alloc(ctx, rounds));
+        VK_TRY(dR.alloc(ctx, rounds));
+        VK_TRY(dtip.alloc(ctx, 1));
+        VK_TRY(ipa_prove_core(ctx, *k, 0, N, hmg, dt, Cdiff, 1, tr.state.data(), (uint32_t)tr.state.size(), "multiproof", dL, dR,
+                              dtip, dyo));
+        VK_TRY(download(ctx, L, dL.p, rounds));
+        VK_TRY(download(ctx, R, dR.p, rounds));
+        VK_TRY(download(ctx, tip, dtip.p, 1));
+    } else {
+        VK_TRY(dL.alloc(ctx, 1));
+        VK_TRY(kzg_open_core(ctx, *k, hmg, N, 0, dt, 1, dL, dyo, true));
+        VK_TRY(download(ctx, L, dL.p, 1));
+    }
+    VK_TRY(download(ctx, yout, dyo.p, 1));
+    return stream_sync(ctx);
+}
+
+int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* C, const uint64_t* z, const vkzg_fr* y,
+                                   uint64_t m, const vkzg_g1_affine* D, const vkzg_g1_affine* L, const vkzg_g1_affine* R,
+                                   const vkzg_fr* tip, const vkzg_fr* yproof, int32_t* ok) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || !k->has_q) return VKZG_ERR_ARG;
+    if (!m || !C || !z || !y || !D || !L || !R || !tip || !yproof || !ok) return VKZG_ERR_ARG;
+    const uint32_t N = k->n, rounds = k->log2n;
+    if (N & (N - 1)) return VKZG_ERR_UNSUPPORTED;
+    for (uint64_t q = 0; q < m; ++q)
+        if (z[q] >= N) return VKZG_ERR_RANGE;  // reference: inversions[query.z] out of bounds (multiproof.rs:198)
+    cudaStream_t s = ctx->stream;
+    DevBuf<affine_t> dC, dD, dE, Cdiff, dL, dR;
+    VK_TRY(upload(ctx, dC, C, m));
+    HostTranscript tr("multiproof");
+    tr.state.reserve(m * 75 + 64);
+    for (uint64_t q = 0; q < m; ++q) {
+        tr.append_point(((const affine_t*)C)[q], "C");
+        tr.append_u64(z[q], "z");
+        tr.append_fr(((const fp_t*)y)[q], "y");
+    }
+    fp_t r = tr.digest("r");
+    tr.append_point(*(const affine_t*)D, "D");
+    fp_t t = tr.digest("t");
+    // e_coeff_q = r^q / (t - z_q)   (multiproof.rs:196-199); E = sum_q e_coeff_q C_q  (:211)
+    std::vector<fp_t> zq(m);
+    for (uint64_t q = 0; q < m; ++q) zq[q] = fp_from_u32<S>((uint32_t)z[q]);
+    DevBuf<fp_t> dzq, rpow, inv, coef, dt, dtip, dy;
+    DevBuf<int32_t> dok;
+    VK_TRY(upload(ctx, dzq, zq.data(), m));
+    VK_TRY(rpow.alloc(ctx, m));
+    VK_TRY(inv.alloc(ctx, m));
+    VK_TRY(dE.alloc(ctx, 1));
+    VK_TRY(Cdiff.alloc(ctx, 1));
+    k_powers<<<ceil_div_u64(m, 128), 128, 0, s>>>(r, m, rpow);
+    VK_TRY(launch_check(ctx));
+    k_mp_inv<<<ceil_div_u64(m, 64), 64, 0, s>>>(t, dzq, (uint32_t)m, inv);
+    VK_TRY(launch_check(ctx));
+    VK_TRY(fr_mul_elementwise(ctx, rpow, inv, m, rpow));
+    VK_TRY(var_base_msm(ctx, dC, rpow, m, dE));
+    VK_TRY(upload(ctx, dD, D, 1));
+    k_point_sub<<<1, 1, 0, s>>>(dE.p, dD.p, Cdiff);
+    VK_TRY(launch_check(ctx));
+    affine_t hE;
+    VK_TRY(download(ctx, &hE, dE.p, 1));
+    VK_TRY(stream_sync(ctx));
+    tr.append_point(hE, "E");
+    VK_TRY(upload(ctx, dt, &t, 1));
+    VK_TRY(upload(ctx, dL, L, rounds));
+    VK_TRY(upload(ctx, dR, R, rounds));
+    VK_TRY(upload(ctx, dtip, tip, 1));
+    VK_TRY(upload(ctx, dy, yproof, 1));
+    VK_TRY(dok.alloc(ctx, 1));
+    VK_TRY(ipa_verify_core(ctx, *k, dt, Cdiff, 1, tr.state.data(), (uint32_t)tr.state.size(), "multiproof", dL, dR, dtip, dy, dok));
+    VK_TRY(download(ctx, ok, dok.p, 1));
+    return stream_sync(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// E1 / K1 / K2 / K3: evaluation-form polynomial work of the reference, batched over B openings, one
+// warp per opening.
+//   LagrangeBasis::evaluate                       lagrange_basis.rs:63-83   (3-way branch, quirk Q2)
+//   LagrangeBasis::divide_by_vanishing            lagrange_basis.rs:91-119  (in-domain quotient)
+//   LagrangeBasis::divive_by_vanishing_outside... lagrange_basis.rs:121-142
+//   KZG::prove_point                              kzg/mod.rs:136-154        (quotient, then M1 over the SRS)
+// The reference spends two field inversions per element in the in-domain quotient; every one of those
+// denominators is a difference of two roots of unity, w^i - w^j = w^j (w^(i-j) - 1), so a key-load table
+// of 1/(w^d - 1) replaces them (field arithmetic is exact: the products are the same field elements).
+// Shapes: data rows hold `len` evaluations (LagrangeBasis::from_vec: domain size Dn = next_pow2(len));
+// the key's precompute has size N with domain next_pow2(N).  The reference indexes out of bounds unless
+// Dn <= N, so that is required here.
+#include "vk_common.cuh"
+
+namespace vk {
+
+int32_t build_domain(vkzg_ctx* ctx, uint32_t log2n, uint32_t size_n, DomainTables& d);
+
+__device__ __forceinline__ fp_t shfl_xor_fp2(const fp_t& v, int mask) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], mask);
+    return r;
+}
+__device__ __forceinline__ fp_t warp_sum_fr2(fp_t v) {
+#pragma unroll 1
+    for (int m = 16; m > 0; m >>= 1) v = fp_add<S>(v, shfl_xor_fp2(v, m));
+    return v;
+}
+
+struct PolyArgs {
+    const fp_t* f;       // [B][len]
+    const fp_t* points;  // [B]
+    uint64_t B;
+    uint32_t len, Dn;    // data row length, data domain size
+    uint32_t N, Np;      // key size, key domain size
+    const fp_t *wD, *wD_inv, *dD_inv;  // data-domain tables
+    const fp_t* wK;                    // key-domain w^i
+    fp_t n_inv;                        // 1 / N
+    fp_t* q;             // [B][Dn] or nullptr (evaluate only)
+    fp_t* scratch;       // [B][len] when q == nullptr
+    fp_t* y;             // [B]
+    int32_t* err;        // set to 1 if a row hits the reference's out-of-bounds panic
+};
+
+__global__ void __launch_bounds__(128) k_poly(PolyArgs A) {
+    uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (p >= A.B) return;
+    const fp_t* f = A.f + p * A.len;
+    fp_t* row = A.q ? A.q + p * A.Dn : A.scratch + p * A.len;
+    const fp_t z = fp_load_ro(A.points + p);
+    const fp_t zc = fp_from_mont<S>(z);
+    const bool small = (zc.l[1] | zc.l[2] | zc.l[3] | zc.l[4] | zc.l[5] | zc.l[6] | zc.l[7]) == 0;
+    const uint32_t zi = zc.l[0];
+
+    // ---- evaluate (lagrange_basis.rs:63-72)
+    fp_t y;
+    if (small && zi <= A.len - 1) {
+        y = fp_load_ro(f + zi);
+    } else if (small && zi <= A.Dn) {
+        y = fp_zero<S>();
+    } else if (small && zi < A.N) {
+        // barycentric coefficients are the unit vector e_zi (precompute.rs:74-78); zi > Dn >= len here
+        y = fp_zero<S>();
+    } else {
+        // t * sum_i f_i w^i / (z - w^i) over the key's domain (precompute.rs:80-87), i < min(len, N) = len
+        fp_t zp = fp_one<S>();
+        for (int b = 31 - __clz(A.N); b >= 0; --b) {
+            zp = fp_mul_ni<S>(zp, zp);
+            if ((A.N >> b) & 1) zp = fp_mul_ni<S>(zp, z);
+        }
+        fp_t t = fp_mul_ni<S>(fp_sub<S>(zp, fp_one<S>()), A.n_inv);
+        fp_t run = fp_one<S>();
+        for (uint32_t i = lane; i < A.len; i += 32) {
+            fp_store(row + i, run);
+            run = fp_mul_ni<S>(run, fp_sub<S>(z, fp_load_ro(A.wK + i)));
+        }
+        fp_t inv = fp_inv<S>(run);
+        fp_t acc = fp_zero<S>();
+        uint32_t cnt = A.len > lane ? (A.len - lane + 31) / 32 : 0;
+        for (uint32_t k = cnt; k-- > 0;) {
+            uint32_t i = lane + 32 * k;
+            fp_t wi = fp_load_ro(A.wK + i);
+            fp_t dinv = fp_mul_ni<S>(inv, fp_load(row + i));
+            inv = fp_mul_ni<S>(inv, fp_sub<S>(z, wi));
+            acc = fp_add<S>(acc, fp_mul_ni<S>(fp_mul_ni<S>(fp_load_ro(f + i), wi), dinv));
+        }
+        y = fp_mul_ni<S>(warp_sum_fr2(acc), t);
+        __syncwarp();
+    }
+    if (lane == 0) fp_store(A.y + p, y);
+    if (!A.q) return;
+
+    if (small && zi <= A.N) {
+        // ---- in-domain quotient (kzg/mod.rs:144-146 -> lagrange_basis.rs:91-119)
+        const uint32_t idx = zi;
+        if (idx >= A.N || idx >= A.Dn) {  // reference: index out of bounds panic (quirk Q2)
+            for (uint32_t i = lane; i < A.Dn; i += 32) fp_store(row + i, fp_zero<S>());
+            if (lane == 0) *A.err = 1;
+            return;
+        }
+        const fp_t eval = idx < A.len ? fp_load_ro(f + idx) : fp_zero<S>();
+        const fp_t w_inv_idx = fp_load_ro(A.wD_inv + idx);
+        fp_t diag = fp_zero<S>();
+        for (uint32_t i = lane; i < A.Dn; i += 32) {
+            if (i == idx) continue;
+            fp_t fi = i < A.len ? fp_load_ro(f + i) : fp_zero<S>();
+            fp_t sub = fp_sub<S>(fi, eval);
+            // 1 / (w^i - w^idx) = w^-idx / (w^(i-idx) - 1)
+            fp_t qi = fp_mul_ni<S>(fp_mul_ni<S>(sub, w_inv_idx), fp_load_ro(A.dD_inv + ((i - idx) & (A.Dn - 1))));
+            fp_store(row + i, qi);
+            // A'(w^idx) / A'(w^i) = w_K^(i-idx);  1/(w^idx - w^i) = -1/(w^i - w^idx)
+            diag = fp_sub<S>(diag, fp_mul_ni<S>(qi, fp_load_ro(A.wK + ((i - idx) & (A.Np - 1)))));
+        }
+        diag = warp_sum_fr2(diag);
+        if (lane == 0) fp_store(row + idx, diag);
+    } else {
+        // ---- outside-domain quotient (lagrange_basis.rs:121-142); zero denominators stay zero like
+        //      ark_ff::batch_inversion
+        __syncwarp();
+        fp_t run = fp_one<S>();
+        for (uint32_t i = lane; i < A.Dn; i += 32) {
+            fp_store(row + i, run);
+            fp_t d = fp_sub<S>(fp_load_ro(A.wD + i), z);
+            if (!fp_is_zero(d)) run = fp_mul_ni<S>(run, d);
+        }
+        fp_t inv = fp_inv<S>(run);
+        uint32_t cnt = A.Dn > lane ? (A.Dn - lane + 31) / 32 : 0;
+        for (uint32_t k = cnt; k-- > 0;) {
+            uint32_t i = lane + 32 * k;
+            fp_t d = fp_sub<S>(fp_load_ro(A.wD + i), z);
+            fp_t qi = fp_zero<S>();
+            if (!fp_is_zero(d)) {
+                fp_t dinv = fp_mul_ni<S>(inv, fp_load(row + i));
+                inv = fp_mul_ni<S>(inv, d);
+                fp_t fi = i < A.len ? fp_load_ro(f + i) : fp_zero<S>();
+                qi = fp_mul_ni<S>(fp_sub<S>(fi, y), dinv);
+            }
+            fp_store(row + i, qi);
+        }
+    }
+}
+
+static int32_t data_domain(vkzg_ctx* ctx, const Key& k, uint32_t len, uint32_t domain_n, uint32_t& Dn, const DomainTables*& dt) {
+    uint32_t lg = 0;
+    uint32_t want = domain_n ? domain_n : len;
+    if (want < len) return VKZG_ERR_ARG;
+    while ((1u << lg) < want) ++lg;
+    Dn = 1u << lg;
+    if (Dn == k.domain_n) {
+        dt = &k.dom;
+        return VKZG_OK;
+    }
+    auto it = ctx->domains.find(lg);
+    if (it == ctx->domains.end()) {
+        DomainTables d;
+        VK_TRY(build_domain(ctx, lg, Dn, d));
+        it = ctx->domains.emplace(lg, d).first;
+    }
+    dt = &it->second;
+    return VKZG_OK;
+}
+
+// q == nullptr: evaluate only.  Returns VKZG_ERR_RANGE (after synchronising) if check_err and a row panicked.
+int32_t poly_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points, uint64_t B,
+                   fp_t* d_q, fp_t* d_y, bool check_err) {
+    if (B == 0) return VKZG_OK;
+    if (len == 0 || len > k.n) return VKZG_ERR_RANGE;
+    uint32_t Dn;
+    const DomainTables* dt;
+    VK_TRY(data_domain(ctx, k, len, domain_n, Dn, dt));
+    if (Dn > k.n) return VKZG_ERR_UNSUPPORTED;
+    DevBuf<fp_t> scratch;
+    DevBuf<int32_t> err;
+    if (!d_q) VK_TRY(scratch.alloc(ctx, B * len));
+    VK_TRY(err.alloc(ctx, 1));
+    VK_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int32_t), ctx->stream));
+    PolyArgs A;
+    A.f = d_f;
+    A.points = d_points;
+    A.B = B;
+    A.len = len;
+    A.Dn = Dn;
+    A.N = k.n;
+    A.Np = k.domain_n;
+    A.wD = dt->omega;
+    A.wD_inv = dt->omega_inv;
+    A.dD_inv = dt->diff_inv;
+    A.wK = k.dom.omega;
+    A.n_inv = k.dom.n_inv;
+    A.q = d_q;
+    A.scratch = scratch.p;
+    A.y = d_y;
+    A.err = err.p;
+    k_poly<<<ceil_div_u64(B * 32, 128), 128, 0, ctx->stream>>>(A);
+    VK_TRY(launch_check(ctx));
+    if (check_err) {
+        int32_t h = 0;
+        VK_CUDA(cudaMemcpyAsync(&h, err.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        VK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h) return VKZG_ERR_RANGE;
+    }
+    return VKZG_OK;
+}
+
+uint32_t data_domain_size(uint32_t len, uint32_t domain_n) {
+    uint32_t want = domain_n > len ? domain_n : len;
+    uint32_t d = 1;
+    while (d < want) d <<= 1;
+    return d;
+}
+
+int32_t kzg_open_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points,
+                      uint64_t B, affine_t* d_proof, fp_t* d_y, bool check_err) {
+    if (B == 0) return VKZG_OK;
+    uint32_t Dn = data_domain_size(len, domain_n);
+    if (Dn > k.n) return VKZG_ERR_UNSUPPORTED;
+    DevBuf<fp_t> q;
+    DevBuf<xyzz_t> acc;
+    VK_TRY(q.alloc(ctx, B * Dn));
+    VK_TRY(acc.alloc(ctx, B));
+    VK_TRY(poly_batch(ctx, k, d_f, len, domain_n, d_points, B, q, d_y, check_err));
+    VK_TRY(fixed_base_msm(ctx, k, q, Dn, B, 0, 0xffffffffu, acc));  // inner_product zips Dn <= N terms
+    return normalize_points(ctx, acc, B, d_proof);
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" {
+
+int32_t vkzg_evaluate_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n, const vkzg_fr* points,
+                            uint64_t B, vkzg_fr* out) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!f || !points || !out))) return VKZG_ERR_ARG;
+    DevBuf<fp_t> df, dp, dy;
+    VK_TRY(upload(ctx, df, f, B * len));
+    VK_TRY(upload(ctx, dp, points, B));
+    VK_TRY(dy.alloc(ctx, B));
+    VK_TRY(poly_batch(ctx, *k, df, len, domain_n, dp, B, nullptr, dy, false));
+    VK_TRY(download(ctx, out, dy.p, B));
+    return stream_sync(ctx);
+}
+
+int32_t vkzg_quotient_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n, const vkzg_fr* points,
+                            uint64_t B, vkzg_fr* out, vkzg_fr* y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!f || !points || !out || !y))) return VKZG_ERR_ARG;
+    if (len == 0 || len > k->n) return VKZG_ERR_RANGE;
+    uint32_t Dn = data_domain_size(len, domain_n);
+    DevBuf<fp_t> df, dp, dq, dy;
+    VK_TRY(upload(ctx, df, f, B * len));
+    VK_TRY(upload(ctx, dp, points, B));
+    VK_TRY(dq.alloc(ctx, B * Dn));
+    VK_TRY(dy.alloc(ctx, B));
+    VK_TRY(poly_batch(ctx, *k, df, len, domain_n, dp, B, dq, dy, true));
+    VK_TRY(download(ctx, out, dq.p, B * Dn));
+    VK_TRY(download(ctx, y, dy.p, B));
+    return stream_sync(ctx);
+}
+
+int32_t vkzg_kzg_open_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
+                                const vkzg_fr* d_points, uint64_t B, vkzg_g1_affine* d_proof, vkzg_fr* d_y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!d_f || !d_points || !d_proof || !d_y))) return VKZG_ERR_ARG;
+    if (len == 0 || len > k->n) return VKZG_ERR_RANGE;
+    return kzg_open_core(ctx, *k, (const fp_t*)d_f, len, domain_n, (const fp_t*)d_points, B, (affine_t*)d_proof, (fp_t*)d_y, false);
+}
+
+int32_t vkzg_kzg_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n, const vkzg_fr* points,
+                            uint64_t B, vkzg_g1_affine* proof, vkzg_fr* y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!f || !points || !proof || !y))) return VKZG_ERR_ARG;
+    if (len == 0 || len > k->n) return VKZG_ERR_RANGE;
+    DevBuf<fp_t> df, dp, dy;
+    DevBuf<affine_t> dpr;
+    VK_TRY(upload(ctx, df, f, B * len));
+    VK_TRY(upload(ctx, dp, points, B));
+    VK_TRY(dpr.alloc(ctx, B));
+    VK_TRY(dy.alloc(ctx, B));
+    VK_TRY(kzg_open_core(ctx, *k, df, len, domain_n, dp, B, dpr, dy, true));
+    VK_TRY(download(ctx, proof, dpr.p, B));
+    VK_TRY(download(ctx, y, dy.p, B));
+    return stream_sync(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// T1: Node::gen_commitment (verkle-tree/src/node.rs:212-277), level-synchronous.
+//
+// The reference walks the tree depth first and commits every node with a dense width-256 vector that is
+// almost entirely zero.  A parent's scalars are to_data_item(child commitment) (lib.rs:56-67), so nodes of
+// one depth are independent: the tree is committed one LEVEL per launch pair, leaves first, each node a
+// sparse term list (slot, scalar):
+//   k_tree_scalars    per term: the literal scalar, or to_data_item of the child's commitment from the
+//                     previous level (affine -> compressed bytes -> mod r)
+//   k_fixed_base_msm  (commit.cu, CSR mode) one warp per node over the key's window tables
+//   k_normalize       batched affine normalisation (shared inversions)
+// The host flattens the pointer tree into these per-level CSR arrays (verkle_kzg_b200/tree.py mirrors
+// Node::insert); the HashMap iteration-order dependence of the reference's extension layout (quirk Q6)
+// never reaches the device, which only sees explicit slots.
+#include "vk_common.cuh"
+
+namespace vk {
+
+__global__ void __launch_bounds__(128) k_tree_scalars(const int32_t* __restrict__ child, const fp_t* __restrict__ lit,
+                                                      const affine_t* __restrict__ prev, uint64_t n_terms, fp_t* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_terms) return;
+    int32_t c = child[t];
+    fp_t r;
+    if (c < 0) {
+        r = fp_load_ro(lit + t);
+    } else {
+        affine_t p;
+        p.x = fp_load(&prev[c].x);
+        p.y = fp_load(&prev[c].y);
+        r = fp_zero<S>();
+        if (!affine_is_inf(p)) {
+            fp_t v, r2;
+            affine_compress(p, v.l);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r2.l[k] = S::r2(k);
+            r = fp_mul<S>(r2, v);
+        }
+    }
+    fp_store(out + t, r);
+}
+
+int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint64_t n_nodes, const uint16_t* d_slot,
+                   const int32_t* d_child, const fp_t* d_lit, uint64_t n_terms, const affine_t* d_prev, affine_t* d_out) {
+    if (n_nodes == 0) return VKZG_OK;
+    DevBuf<fp_t> sc;
+    DevBuf<xyzz_t> acc;
+    VK_TRY(sc.alloc(ctx, n_terms));
+    VK_TRY(acc.alloc(ctx, n_nodes));
+    if (n_terms) {
+        k_tree_scalars<<<ceil_div_u64(n_terms, 128), 128, 0, ctx->stream>>>(d_child, d_lit, d_prev, n_terms, sc);
+        VK_TRY(launch_check(ctx));
+    }
+    VK_TRY(fixed_base_msm_csr(ctx, k, sc, 0, n_nodes, 0, 0xffffffffu, d_row_ptr, d_slot, acc));
+    return normalize_points(ctx, acc, n_nodes, d_out);
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" {
+
+int32_t vkzg_tree_level_dev(vkzg_ctx* ctx, uint32_t key_id, const uint32_t* d_row_ptr, uint64_t n_nodes, const uint16_t* d_slot,
+                            const int32_t* d_child, const vkzg_fr* d_lit, uint64_t n_terms, const vkzg_g1_affine* d_prev,
+                            vkzg_g1_affine* d_out) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
+    if (n_nodes && (!d_row_ptr || !d_out)) return VKZG_ERR_ARG;
+    if (n_terms && (!d_slot || !d_child || !d_lit)) return VKZG_ERR_ARG;
+    return tree_level(ctx, *k, d_row_ptr, n_nodes, d_slot, d_child, (const fp_t*)d_lit, n_terms, (const affine_t*)d_prev,
+                      (affine_t*)d_out);
+}
+
+int32_t vkzg_tree_commit_levels(vkzg_ctx* ctx, uint32_t key_id, uint32_t n_levels, const uint64_t* nodes_per_level,
+                                const uint32_t* const* row_ptr, const uint16_t* const* slot, const int32_t* const* child,
+                                const vkzg_fr* const* lit, vkzg_g1_affine* root_out) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
+    if (!n_levels || !nodes_per_level || !row_ptr || !slot || !child || !lit || !root_out) return VKZG_ERR_ARG;
+    if (nodes_per_level[n_levels - 1] != 1) return VKZG_ERR_ARG;  // the last level is the root
+    // validate on the host: slots inside the key, children among the nodes of earlier levels
+    uint64_t total_nodes = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        uint64_t nn = nodes_per_level[l];
+        if (!row_ptr[l]) return VKZG_ERR_ARG;
+        uint64_t nt = row_ptr[l][nn];
+        for (uint64_t t = 0; t < nt; ++t) {
+            if (slot[l][t] >= k->n) return VKZG_ERR_RANGE;
+            if (child[l][t] >= 0 && (uint64_t)child[l][t] >= total_nodes) return VKZG_ERR_RANGE;
+        }
+        total_nodes += nn;
+    }
+    if (total_nodes >= (1ull << 31)) return VKZG_ERR_RANGE;
+    DevBuf<affine_t> all;
+    VK_TRY(all.alloc(ctx, total_nodes));
+    uint64_t off = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) {
+        uint64_t nn = nodes_per_level[l];
+        uint64_t nt = row_ptr[l][nn];
+        DevBuf<uint32_t> d_rp;
+        DevBuf<uint16_t> d_sl;
+        DevBuf<int32_t> d_ch;
+        DevBuf<fp_t> d_li;
+        VK_TRY(upload(ctx, d_rp, row_ptr[l], nn + 1));
+        VK_TRY(upload(ctx, d_sl, slot[l], nt));
+        VK_TRY(upload(ctx, d_ch, child[l], nt));
+        VK_TRY(upload(ctx, d_li, lit[l], nt));
+        VK_TRY(tree_level(ctx, *k, d_rp, nn, d_sl, d_ch, d_li, nt, all.p, all.p + off));
+        off += nn;
+    }
+    const affine_t* a = all.p + (total_nodes - 1);
+    VK_TRY(download(ctx, root_out, a, 1));
+    return stream_sync(ctx);
+}
+
+}  // extern "C"
