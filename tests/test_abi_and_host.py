@@ -1,0 +1,161 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/vkzg.h declares
+(no compute without a GPU), fails loudly without a device, and the host-side tree flattening / sharding logic
+is right (checked by evaluating the level lists with the ORACLE's commit on the CPU)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def vk():
+    import verkle_kzg_b200
+    verkle_kzg_b200.build()
+    return verkle_kzg_b200
+
+
+def test_library_exports_every_declared_symbol(vk):
+    hdr = open(os.path.join(ROOT, "include", "vkzg.h")).read()
+    names = sorted(set(re.findall(r"\b(vkzg_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    lib = vk._lib.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.vkzg_abi_version() == 1
+    assert b"no CPU fallback" in lib.vkzg_strerror(ctypes.c_int32(-1))
+
+
+def test_no_cpu_fallback(vk):
+    """without a usable sm_100 device every entry point refuses: there is nothing behind the library"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(vk.VkzgError):
+        vk.Engine(0)
+    assert vk._lib.lib().vkzg_commit_batch(None, 0, None, 0, ctypes.c_uint64(0), None) != 0
+
+
+def test_product_does_not_import_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's CPU arm may touch oracle/"""
+    pkg = os.path.join(ROOT, "verkle_kzg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in src and "import orc" not in src and "oracle/" not in src, f
+
+
+def _oracle_eval_levels(bases, levels):
+    """commit every node of the flattened tree with the oracle (CPU), leaves first"""
+    nodes = []
+    for lv in levels:
+        rp, slot, child, lit = lv["row_ptr"], lv["slot"], lv["child"], lv["lit"]
+        for j in range(len(rp) - 1):
+            vec = np.zeros((256, 32), dtype=np.uint8)
+            for t in range(rp[j], rp[j + 1]):
+                vec[slot[t]] = lit[t] if child[t] < 0 else orc.to_data_item(nodes[child[t]])[0]
+            nodes.append(orc.msm(bases, vec))
+    return nodes[-1]
+
+
+@pytest.mark.parametrize("n,key_len,width,hi", [(1, 32, 256, 256), (25, 32, 256, 256), (40, 4, 256, 3), (30, 3, 3, 256)])
+def test_tree_flattening_matches_reference_structure(n, key_len, width, hi):
+    from verkle_kzg_b200.tree import VerkleTree
+    rng = np.random.default_rng(n * 7 + key_len)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, 256)
+    keys = rng.integers(0, hi, (n, key_len), dtype=np.uint8)
+    _, first = np.unique(keys[:, : key_len - 1], axis=0, return_index=True)
+    keys = keys[np.sort(first)]
+    vals = rng.integers(0, 256, (len(keys), 32), dtype=np.uint8)
+    t = VerkleTree(key_len, ext_width=width)
+    for k, v in zip(keys, vals):
+        t.insert_single(k, v)
+    levels = t.levels()
+    assert len(levels[-1]["row_ptr"]) == 2  # the root alone in the last level
+    total = 0
+    for lv in levels:  # children only reference earlier nodes
+        assert (lv["child"] < total).all()
+        total += len(lv["row_ptr"]) - 1
+    assert (_oracle_eval_levels(bases, levels) == orc.tree_commit(bases, keys, vals, ext_width=width)).all()
+    assert t.get_single(keys[-1]) == bytes(vals[-1])
+
+
+def test_tree_insert_differing_last_unit_panics_like_the_reference():
+    from verkle_kzg_b200.tree import VerkleTree
+    t = VerkleTree(3)
+    t.insert_single(bytes([1, 2, 3]), bytes(32))
+    t.insert_single(bytes([1, 5, 6]), bytes(32))       # internal node under root child 1, keyed on unit 1
+    with pytest.raises(ValueError):                     # node.rs:163-165 at cur_depth == N - 2, then :139-141
+        t.insert_single(bytes([1, 2, 9]), bytes(32))
+    keys = np.array([[1, 2, 3], [1, 5, 6], [1, 2, 9]], dtype=np.uint8)
+    with pytest.raises(AssertionError):                 # the oracle's literal restatement throws on the same sequence
+        orc.tree_commit(orc.points_walk(1, 1, 4), keys, np.zeros((3, 32), dtype=np.uint8), ext_width=3)
+
+
+def test_split_range():
+    from verkle_kzg_b200.sharding import split_range
+    for total in (0, 1, 7, 8, 1 << 20, (1 << 14) + 3):
+        for world in (1, 2, 3, 8):
+            parts = [split_range(total, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == total
+            for (f0, c0), (f1, _) in zip(parts, parts[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import orc
+from verkle_kzg_b200.sharding import split_range, all_gather_points
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(5)
+k0, k1 = orc.rand_fr(rng, 2)
+n = 37
+bases = orc.points_walk(k0, k1, n)
+s = orc.rand_fr_buf(rng, n)
+first, cnt = split_range(n, world, rank)
+part = orc.msm(bases[first:first + cnt], s[first:first + cnt]) if cnt else np.zeros(64, dtype=np.uint8)
+allp = all_gather_points(dist, torch, torch.from_numpy(part.copy()))
+acc = np.zeros(64, dtype=np.uint8)
+for r in range(world):
+    acc = orc.g1_add(acc, allp[r, 0].numpy())
+assert (acc == orc.msm(bases, s)).all()
+# batch sharding: every rank commits its slice, results gathered in rank order equal the whole batch
+B = 5
+a = orc.rand_fr_buf(rng, B * 4).reshape(B, 4, 32)
+f, c = split_range(B, world, rank)
+mine = orc.commit_batch(bases[:4], a[f:f + c]) if c else np.zeros((0, 64), dtype=np.uint8)
+sizes = [split_range(B, world, r)[1] for r in range(world)]
+pad = np.zeros((max(sizes), 64), dtype=np.uint8); pad[:c] = mine
+g = all_gather_points(dist, torch, torch.from_numpy(pad))
+got = np.concatenate([g[r, :sizes[r]].numpy() for r in range(world)])
+assert (got == orc.commit_batch(bases[:4], a)).all()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_msm_and_batches_over_gloo_world2(tmp_path):
+    """the N > 1 path on CPU: point-range sharded MSM combined by all_gather + point addition, and batch sharding,
+    with the oracle standing in for the device kernels (gloo, world_size 2)"""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29531", str(script), ROOT], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
