@@ -48,7 +48,7 @@ __device__ __forceinline__ void emit_entries(const fp_t& k, uint32_t row_base /*
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     k_fixed_base_msm(const affine_t* __restrict__ table, uint32_t c, uint32_t W, const fp_t* __restrict__ scalars, uint32_t T,
                      uint64_t jobs, uint32_t ipa_m, uint32_t q_row, const uint32_t* __restrict__ row_ptr,
                      const uint16_t* __restrict__ slot, xyzz_t* __restrict__ out) {
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                 nxt = load_affine_ro(table + (en & 0x7fffffffu));
             }
             if (e >> 31) cur.y = fp_neg<Q>(cur.y);
-            xyzz_madd(acc, cur);
+            xyzz_madd_hot(acc, cur);
             cur = nxt;
             e = en;
             t = tn;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1) {
         xyzz_t o = shfl_down_xyzz(acc, off);
-        if (lane < (uint32_t)off) acc = xyzz_add(acc, o);
+        if (lane < (uint32_t)off) acc = xyzz_add_ni(acc, o);
     }
     if (lane == 0) {
         fp_store(&out[job].x, acc.x);
@@ -131,6 +131,7 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
     static bool attr_set = false;
     if (!attr_set) {
         VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     uint64_t blocks = (jobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;

@@ -85,7 +85,7 @@ __device__ __forceinline__ xyzz_t shfl_xor_xyzz(const xyzz_t& v, int mask) {
 }
 
 // P (power of two <= 32) adjacent lanes per bucket
-__global__ void __launch_bounds__(128) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                     const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P,
                                                     xyzz_t* __restrict__ buckets) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) k_msm_bucket(const affine_t* __restrict__
             nxt = load_affine_ro2(table + (en & 0x7fffffffu));
         }
         if (e >> 31) cur.y = fp_neg<Q>(cur.y);
-        xyzz_madd(acc, cur);
+        xyzz_madd_hot(acc, cur);
         cur = nxt;
         e = en;
         i = in;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) k_msm_bucket(const affine_t* __restrict__
 #pragma unroll 1
     for (uint32_t m = 1; m < P; m <<= 1) {
         xyzz_t o = shfl_xor_xyzz(acc, (int)m);
-        acc = xyzz_add(acc, o);
+        acc = xyzz_add_ni(acc, o);
     }
     if (live && p == 0) {
         fp_store(&buckets[b].x, acc.x);
