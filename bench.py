@@ -402,8 +402,89 @@ def run_native(args):
                "points_per_gpu": per}
         cpu_fn = cpu_msm_sample
         bases_h = None
+    elif wl == "multiproof":
+        m = args.batch or (1 << 12)                                             # configs[2]: 2^12 openings aggregated
+        bases = make_points_dev(torch, eng, N_WIDTH + 1, gen)
+        key = eng.load_key_dev(bases, N_WIDTH, d_q=bases[N_WIDTH:], window_bits=WINDOW_BITS)
+        gen.manual_seed(0x5EED3000 + rank)
+        f = rand_fr_dev(torch, m * N_WIDTH, gen).reshape(m, N_WIDTH, 32)
+        zi = torch.randint(0, N_WIDTH, (m,), device="cuda", generator=gen)
+        Cq = torch.empty((m, 64), dtype=torch.uint8, device="cuda")
+        eng.commit_batch_dev(key, f, N_WIDTH, m, Cq)
+        yq = f[torch.arange(m, device="cuda"), zi].contiguous()
+        f_h = pinned(torch, (m, N_WIDTH, 32))
+        f_h.copy_(f)
+        C_h, y_h = Cq.cpu().contiguous(), yq.cpu().contiguous()
+        z_h = zi.cpu().numpy().astype(np.uint64)
+        D_h, L_h, R_h = pinned(torch, (64,)), pinned(torch, (8, 64)), pinned(torch, (8, 64))
+        tip_h, yo_h = pinned(torch, (32,)), pinned(torch, (32,))
+        kid = ctypes.c_uint32(key.id)
+        zp = z_h.ctypes.data_as(ctypes.c_void_p)
+
+        def step():
+            check(L.vkzg_multiproof_prove_dev(eng._ctx, kid, ctypes.c_int32(0), ctypes.c_void_p(f.data_ptr()), hp(C_h), zp, hp(y_h),
+                                              ctypes.c_uint64(m), hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_dev")
+
+        def step_e2e():
+            check(L.vkzg_multiproof_prove(eng._ctx, kid, ctypes.c_int32(0), hp(f_h), hp(C_h), zp, hp(y_h), ctypes.c_uint64(m), hp(D_h),
+                                          hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof")
+        madds_per_unit = (2 * N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * WINDOWS   # D, E commits + the final IPA opening
+        launches_timed = 10
+        units_per_step = 1
+        h2d, d2h = f_h.numel() + m * (64 + 8 + 32), 64 + 2 * 8 * 64 + 64
+        metric, unit = "ipa_multiproofs_per_s", "multiproofs/s"
+        cfg = {"workload": f"configs[2]: IPA multiproof aggregating {m} openings at width 256 (one multiproof per step per GPU; replicas across GPUs)",
+               "openings_per_multiproof": m}
+        cpu_fn = None
+        bases_h = None
+    elif wl == "tree":
+        nkeys = args.batch or (1 << 20)                                         # configs[4]: bulk insert of 2^20 keys
+        from verkle_kzg_b200.tree import build_levels
+        from verkle_kzg_b200.sharding import split_range
+        bases = make_points_dev(torch, eng, N_WIDTH, gen)
+        key = eng.load_key_dev(bases, N_WIDTH, window_bits=WINDOW_BITS)
+        rng = np.random.default_rng(0x5EED0005)
+        keys_all = rng.integers(0, 256, (nkeys, 32), dtype=np.uint8)
+        vals_all = rng.integers(0, 256, (nkeys, 32), dtype=np.uint8)
+        lo, cnt = split_range(256, world, rank)                                 # shard by top-level child index (whole subtrees per rank)
+        sel = (keys_all[:, 0] >= lo) & (keys_all[:, 0] < lo + cnt)
+        t0 = time.perf_counter()
+        levels = build_levels(keys_all[sel], vals_all[sel], 256)                # host pointer structure -> level lists (not timed: out of the path)
+        host_build_s = time.perf_counter() - t0
+        counts = [len(lv["row_ptr"]) - 1 for lv in levels]
+        total_nodes = sum(counts)
+        dev = [dict(rp=torch.from_numpy(lv["row_ptr"].astype(np.int32)).cuda(), sl=torch.from_numpy(lv["slot"].astype(np.int16)).cuda(),
+                    ch=torch.from_numpy(lv["child"]).cuda(), li=torch.from_numpy(np.ascontiguousarray(lv["lit"])).cuda(),
+                    n=c, t=len(lv["slot"])) for lv, c in zip(levels, counts)]
+        nodes = torch.empty((total_nodes, 64), dtype=torch.uint8, device="cuda")
+        allp = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
+        root = torch.empty((1, 64), dtype=torch.uint8, device="cuda")
+
+        def step():
+            off = 0
+            for d in dev:
+                eng.tree_level_dev(key, d["rp"], d["n"], d["sl"] if d["t"] else None, d["ch"] if d["t"] else None,
+                                   d["li"] if d["t"] else None, d["t"], nodes, nodes[off:])
+                off += d["n"]
+            if world > 1:   # one exchange at the root: per-rank partial roots (disjoint child slots) are added
+                dist.all_gather_into_tensor(allp, nodes[total_nodes - 1:total_nodes])
+                eng.g1_sum_dev(allp, world, root)
+
+        def step_e2e():
+            eng.tree_commit_levels(key, levels)
+        terms = sum(len(lv["slot"]) for lv in levels)
+        madds_per_unit = terms * WINDOWS / max(1, int(sel.sum()))               # upper bound: zero digits are skipped at run time
+        launches_timed = len(levels)
+        units_per_step = int(sel.sum())
+        h2d = sum(lv["row_ptr"].nbytes + lv["slot"].nbytes + lv["child"].nbytes + lv["lit"].nbytes for lv in levels)
+        d2h = 64
+        metric, unit = "verkle_tree_commit_keys_per_s", "keys/s"
+        cfg = {"workload": f"configs[4]: verkle tree of {nkeys} random 32-byte keys, every node recommitted level by level up to the root",
+               "keys_this_rank": units_per_step, "nodes_per_level": counts, "terms": terms, "host_flatten_seconds_not_timed": round(host_build_s, 1)}
+        cpu_fn = None
+        bases_h = None
     else:
-        raise SystemExit(f"workload {wl}: run tools/bench_extra.py")
+        raise SystemExit(f"unknown workload {wl}")
 
     cfg["l2_policy"] = "inputs and tables exceed the 126 MB L2 (window tables 8.6 GB, scalars >= 128 MB); no flush needed"
     # ---- device-resident timing, with the dominant kernel bracketed by its own event pairs
@@ -415,11 +496,17 @@ def run_native(args):
     launches = eng.launches - l0
     kn, kms = eng.kernel_timing_read()
     eng.kernel_timing(False)
-    total_units = units_per_step * world * args.steps
+    if world > 1:
+        tu = torch.tensor([units_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tu)
+        units_all = float(tu.item())
+    else:
+        units_all = float(units_per_step)
+    total_units = units_all * args.steps
     value = total_units / (ms * 1e-3)
     # ---- end to end through the host-pointer C ABI
     ms_e2e, _ = timed_steps(torch, dist, world, step_e2e, max(1, args.steps // 2), 1)
-    e2e_value = units_per_step * world * max(1, args.steps // 2) / (ms_e2e * 1e-3)
+    e2e_value = units_all * max(1, args.steps // 2) / (ms_e2e * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -429,7 +516,7 @@ def run_native(args):
     achieved = macs_per_launch_set * args.steps / (kms * 1e-3) / 1e12 if kms > 0 else None
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if wl == "msm" else "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if wl in ("msm", "tree") else "weak", "vs_baseline": None,
         "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": cfg,
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

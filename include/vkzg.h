@@ -139,6 +139,11 @@ int32_t vkzg_ipa_prove_commitment_batch(vkzg_ctx* ctx, uint32_t key_id, const vk
 int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
                               const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
                               vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout);
+/* same with the m x N rows already resident in device memory (d_f); the query metadata (C, z, y) and all outputs
+ * stay host pointers because the outer transcript is hashed on the host               */
+int32_t vkzg_multiproof_prove_dev(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* d_f, const vkzg_g1_affine* C,
+                                  const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
+                                  vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout);
 /* ---- P2: verify_multiproof (multiproof.rs:178-215), IPA scheme; *ok = 1/0.  (KZG verification is two
  *      pairings, kzg/mod.rs:165-189, and stays on the host side of the shim.)                            */
 int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* C, const uint64_t* z,

@@ -46,6 +46,8 @@ def test_field_ops(hc, tag, mod):
     assert dec(_op(hc, tag, 6, a)) == [(-x) % mod for x in xs]
     nz = [x for x in xs[:40] + edge if x]
     assert dec(_op(hc, tag, 3, enc(nz))) == [pow(x, -1, mod) for x in nz]
+    assert dec(_op(hc, tag, 7, enc(nz))) == [pow(x, -1, mod) for x in nz]
+    assert dec(_op(hc, tag, 3, enc([0]))) == [0]
     # from_mont gives the canonical integer; to_mont inverts it
     canon = _op(hc, tag, 4, a)
     assert [int.from_bytes(bytes(r), "little") for r in canon] == xs

@@ -1,0 +1,89 @@
+// Do the integer-multiply, ALU and FP64 pipes of sm_100a overlap?  Independent chains of each kind in one warp.
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/pipemix tools/pipemix.cu
+#include <cstdio>
+#include <cstdint>
+template <int NI, int NA, int ND, int NX>  // per inner step: NI mad.wide, NA add (IADD3), ND fma.f64, NX mad.wide with carry chain (pairs)
+__global__ void __launch_bounds__(256) k(uint32_t iters, uint64_t* sink) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a[8], b[8], s[8];
+    uint64_t acc[8], xacc[8];
+    double da[8], dacc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = t * 2654435761u + j * 977 + 1;
+        b[j] = (t ^ 0x9e3779b9u) + j * 131;
+        s[j] = t + j;
+        acc[j] = j + t;
+        xacc[j] = j * 3 + t;
+        da[j] = 1.0 + j * 1e-9 + t * 1e-12;
+        dacc[j] = j;
+    }
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < NI) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(b[(j + r) & 7]));
+                if (j < NA) asm volatile("add.u32 %0, %0, %1;" : "+r"(s[j]) : "r"(a[(j + r) & 7]));
+                if (j < ND) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(dacc[j]) : "d"(da[j]), "d"(da[(j + r) & 7]));
+            }
+            if (NX) {
+                uint32_t lo[4], hi[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { lo[j] = (uint32_t)xacc[j]; hi[j] = (uint32_t)(xacc[j] >> 32); }
+                asm volatile(
+                    "mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                    "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                    "madc.lo.cc.u32 %4, %10, %12, %4;\n\tmadc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                    "madc.lo.cc.u32 %6, %11, %12, %6;\n\tmadc.hi.u32 %7, %11, %12, %7;"
+                    : "+r"(lo[0]), "+r"(hi[0]), "+r"(lo[1]), "+r"(hi[1]), "+r"(lo[2]), "+r"(hi[2]), "+r"(lo[3]), "+r"(hi[3])
+                    : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[r]));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xacc[j] = ((uint64_t)hi[j] << 32) | lo[j];
+            }
+        }
+    }
+    uint64_t x = 0;
+    double ds = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x ^= acc[j] ^ s[j] ^ xacc[j]; ds += dacc[j]; }
+    if (x == 0x123456789abcdefull || ds == 1234.5678) sink[0] = x;
+}
+template <int NI, int NA, int ND, int NX>
+void run(const char* name) {
+    uint64_t* sink;
+    cudaMalloc(&sink, 8);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    int blocks = 148 * 4;
+    uint32_t iters = 4000;
+    k<NI, NA, ND, NX><<<blocks, 256>>>(100, sink);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a);
+        k<NI, NA, ND, NX><<<blocks, 256>>>(iters, sink);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    // cycles per SMSP per inner step (8 inner steps per iteration, 8 warps per SMSP)
+    double cyc = best * 1e-3 * 1.965e9 / (iters * 8.0) / 8.0;
+    printf("%-44s %8.3f ms   %6.2f cycles per warp per inner step (instr/step: %d)\n", name, best, cyc, NI + NA + ND + NX * 4);
+}
+int main() {
+    run<8, 0, 0, 0>("8 mad.wide");
+    run<0, 8, 0, 0>("8 add.u32");
+    run<0, 0, 8, 0>("8 fma.f64");
+    run<8, 8, 0, 0>("8 mad.wide + 8 add.u32");
+    run<8, 0, 8, 0>("8 mad.wide + 8 fma.f64");
+    run<4, 0, 4, 0>("4 mad.wide + 4 fma.f64");
+    run<0, 8, 8, 0>("8 add.u32 + 8 fma.f64");
+    run<0, 0, 0, 1>("carry chain of 4 wide pairs");
+    run<0, 0, 8, 1>("carry chain of 4 + 8 fma.f64");
+    run<0, 8, 0, 1>("carry chain of 4 + 8 add.u32");
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+}

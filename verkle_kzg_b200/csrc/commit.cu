@@ -48,22 +48,43 @@ __device__ __forceinline__ void emit_entries(const fp_t& k, uint32_t row_base /*
     }
 }
 
+__device__ __forceinline__ xyzz_t shfl_xor_xyzz_c(const xyzz_t& v, int mask) {
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], mask);
+        r.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], mask);
+        r.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], mask);
+        r.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], mask);
+    }
+    return r;
+}
+
+// LPJ lanes per job (32, 8 or 4): a warp runs 32 / LPJ jobs side by side, each group of LPJ lanes with its own
+// slice of the shared-memory entry list.  Wide jobs (commits, IPA cross terms) use the whole warp; verkle nodes
+// with a handful of terms use 4 or 8 lanes so that the shuffle-tree fold (log2 LPJ full additions) does not
+// dominate their few table additions.
+template <int LPJ>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     k_fixed_base_msm(const affine_t* __restrict__ table, uint32_t c, uint32_t W, const fp_t* __restrict__ scalars, uint32_t T,
                      uint64_t jobs, uint32_t ipa_m, uint32_t q_row, const uint32_t* __restrict__ row_ptr,
                      const uint16_t* __restrict__ slot, xyzz_t* __restrict__ out) {
     extern __shared__ uint32_t smem[];
+    constexpr uint32_t JPW = 32 / LPJ;                 // jobs per warp
+    constexpr uint32_t CHUNK = CHUNK_TERMS / JPW;      // terms recoded per pass and group
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t list_cap = CHUNK_TERMS * W;
-    uint32_t* list = smem + warp * (list_cap + 32);
-    uint32_t* cnt = list + list_cap;
-    uint64_t job = (uint64_t)blockIdx.x * WARPS_PER_CTA + warp;
-    if (job >= jobs) return;
+    const uint32_t gl = lane % LPJ, grp = lane / LPJ;
+    const uint32_t list_cap = CHUNK * W;
+    uint32_t* list = smem + warp * (CHUNK_TERMS * W + 32) + grp * list_cap;
+    uint32_t* cnt = smem + warp * (CHUNK_TERMS * W + 32) + CHUNK_TERMS * W + grp;
+    uint64_t job = ((uint64_t)blockIdx.x * WARPS_PER_CTA + warp) * JPW + grp;
+    const bool live = job < jobs;
     // dense: job j owns scalars[j*T .. (j+1)*T), term t uses base t.  CSR (row_ptr != nullptr, verkle nodes):
     // job j owns terms [row_ptr[j], row_ptr[j+1]) and term t uses base slot[t].
     const fp_t* sc = scalars + job * T;
     const uint16_t* sl = nullptr;
-    if (row_ptr) {
+    if (!live) T = 0;
+    if (row_ptr && live) {
         uint32_t t0 = row_ptr[job];
         T = row_ptr[job + 1] - t0;
         sc = scalars + t0;
@@ -73,12 +94,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     // half length is ipa_m (see ipa.cu): term j < T-1 uses base (j / m) * 2m + (L ? m : 0) + j % m and the
     // last term the base q_row (when q_row != 0xffffffff)
     const uint32_t side_off = (job & 1) ? 0u : ipa_m;
+    // every lane of the warp runs the same number of passes (the __syncwarp()s below must be convergent)
+    uint32_t Tmax = T;
+    if (JPW > 1) {
+#pragma unroll
+        for (int m = 16; m >= LPJ; m >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, m));
+    }
 
     xyzz_t acc = xyzz_inf();
-    for (uint32_t chunk = 0; chunk < T; chunk += CHUNK_TERMS) {
-        if (lane == 0) *cnt = 0;
+    for (uint32_t chunk = 0; chunk < Tmax; chunk += CHUNK) {
+        if (gl == 0) *cnt = 0;
         __syncwarp();
-        for (uint32_t j = lane; j < CHUNK_TERMS; j += 32) {
+        for (uint32_t j = gl; j < CHUNK; j += LPJ) {
             uint32_t term = chunk + j;
             if (term < T) {
                 fp_t k = fp_from_mont<S>(fp_load_ro(sc + term));
@@ -89,7 +116,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
         }
         __syncwarp();
         const uint32_t n = *cnt;
-        uint32_t t = lane;
+        uint32_t t = gl;
         uint32_t e = 0;
         affine_t cur;
         if (t < n) {
@@ -97,7 +124,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
             cur = load_affine_ro(table + (e & 0x7fffffffu));
         }
         while (t < n) {
-            uint32_t tn = t + 32, en = 0;
+            uint32_t tn = t + LPJ, en = 0;
             affine_t nxt;
             if (tn < n) {
                 en = list[tn];
@@ -112,11 +139,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
         __syncwarp();
     }
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, off);
-        if (lane < (uint32_t)off) acc = xyzz_add_ni(acc, o);
+    for (int off = LPJ / 2; off > 0; off >>= 1) {
+        xyzz_t o = shfl_xor_xyzz_c(acc, off);
+        acc = xyzz_add_ni(acc, o);
     }
-    if (lane == 0) {
+    if (gl == 0 && live) {
         fp_store(&out[job].x, acc.x);
         fp_store(&out[job].y, acc.y);
         fp_store(&out[job].zz, acc.zz);
@@ -124,27 +151,37 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     }
 }
 
-int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
-                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out) {
-    if (jobs == 0) return VKZG_OK;
-    size_t smem = (size_t)WARPS_PER_CTA * (CHUNK_TERMS * k.W + 32) * sizeof(uint32_t);
+template <int LPJ>
+static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
+                                 uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out) {
     static bool attr_set = false;
     if (!attr_set) {
-        VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm<LPJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm<LPJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    uint64_t blocks = (jobs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    size_t smem = (size_t)WARPS_PER_CTA * (CHUNK_TERMS * k.W + 32) * sizeof(uint32_t);
+    uint64_t per_cta = (uint64_t)WARPS_PER_CTA * (32 / LPJ);
+    uint64_t blocks = (jobs + per_cta - 1) / per_cta;
     if (blocks > 0x7fffffffull) return VKZG_ERR_RANGE;
     KernelTimer timer(ctx);
-    k_fixed_base_msm<<<(uint32_t)blocks, WARPS_PER_CTA * 32, smem, ctx->stream>>>(k.table, k.c, k.W, d_scalars, T, jobs, ipa_m,
-                                                                                  q_row, d_row_ptr, d_slot, d_out);
+    k_fixed_base_msm<LPJ><<<(uint32_t)blocks, WARPS_PER_CTA * 32, smem, ctx->stream>>>(k.table, k.c, k.W, d_scalars, T, jobs, ipa_m, q_row,
+                                                                                       d_row_ptr, d_slot, d_out);
     return launch_check(ctx);
+}
+
+// lanes_per_job: 0 = whole warp
+int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
+                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job) {
+    if (jobs == 0) return VKZG_OK;
+    if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, d_out);
+    if (lanes_per_job == 8) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, d_out);
+    return launch_fixed_base<32>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, d_out);
 }
 
 int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                        uint32_t q_row, xyzz_t* d_out) {
-    return fixed_base_msm_csr(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, d_out);
+    return fixed_base_msm_csr(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, d_out, 0);
 }
 
 // -------------------------------------------------------------------------------------------------

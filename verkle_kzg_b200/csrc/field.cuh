@@ -37,6 +37,10 @@ struct FrParams {
         constexpr uint32_t v[8] = {0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
         return v[i];
     }
+    VK_HD static constexpr uint32_t r3(int i) {  // R^3 mod p
+        constexpr uint32_t v[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+        return v[i];
+    }
 };
 
 struct FqParams {
@@ -55,6 +59,10 @@ struct FqParams {
     }
     VK_HD static constexpr uint32_t half(int i) {
         constexpr uint32_t v[8] = {0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+        return v[i];
+    }
+    VK_HD static constexpr uint32_t r3(int i) {  // R^3 mod p
+        constexpr uint32_t v[8] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
         return v[i];
     }
 };
@@ -382,9 +390,10 @@ __host__ __device__ __noinline__ fp_t fp_mul_ni(const fp_t a, const fp_t b) {
     return fp_mul<P>(a, b);
 }
 
-// a^(p-2): Fermat inversion (0 -> 0).  Uniform control flow; ~256 squarings + ~130 multiplies.
+// a^(p-2): Fermat inversion (0 -> 0).  Uniform control flow; ~256 squarings + ~130 multiplies.  Kept as the
+// cross-check of the binary inversion below (tests/host).
 template <class P>
-__host__ __device__ __noinline__ fp_t fp_inv(const fp_t a) {
+__host__ __device__ __noinline__ fp_t fp_inv_fermat(const fp_t a) {
     fp_t acc = fp_one<P>();
 #pragma unroll
     for (int k = 7; k >= 0; --k) {
@@ -396,6 +405,77 @@ __host__ __device__ __noinline__ fp_t fp_inv(const fp_t a) {
         }
     }
     return acc;
+}
+
+// x >>= 1 over 8 limbs (top bit filled with `top`)
+VK_HD void shr1_8(uint32_t* x, uint32_t top) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[7] = (x[7] >> 1) | (top << 31);
+}
+VK_HD bool geq8(const uint32_t* a, const uint32_t* b) {  // a >= b
+    uint32_t t[8];
+    return sub8(t, a, b) == 0;
+}
+
+// Modular inverse by the binary extended Euclidean algorithm on the Montgomery REPRESENTATIVE, then one
+// multiplication by R^3 to land in Montgomery form again: (aR)^-1 * R^3 / R = a^-1 R.   0 -> 0.
+// ~6-7x fewer dependent instructions than the Fermat ladder; data-dependent control flow (only used where one
+// thread per point normalises results).
+template <class P>
+__host__ __device__ __noinline__ fp_t fp_inv(const fp_t a) {
+    if (fp_is_zero(a)) return a;
+    uint32_t u[8], v[8], x1[8], x2[8], pl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u[i] = a.l[i];
+        v[i] = pl[i] = P::p(i);
+        x1[i] = (i == 0);
+        x2[i] = 0;
+    }
+    // invariants: x1 * a == u, x2 * a == v (mod p); u, v odd after the halving loops; x1, x2 in [0, p)
+    for (;;) {
+        while ((u[0] & 1) == 0) {
+            shr1_8(u, 0);
+            if (x1[0] & 1) {
+                uint32_t c = add8(x1, x1, pl);
+                shr1_8(x1, c);
+            } else {
+                shr1_8(x1, 0);
+            }
+        }
+        bool u_one = (u[0] == 1) && ((u[1] | u[2] | u[3] | u[4] | u[5] | u[6] | u[7]) == 0);
+        if (u_one) break;
+        while ((v[0] & 1) == 0) {
+            shr1_8(v, 0);
+            if (x2[0] & 1) {
+                uint32_t c = add8(x2, x2, pl);
+                shr1_8(x2, c);
+            } else {
+                shr1_8(x2, 0);
+            }
+        }
+        bool v_one = (v[0] == 1) && ((v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0);
+        if (v_one) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x1[i] = x2[i];
+            break;
+        }
+        if (geq8(u, v)) {
+            sub8(u, u, v);
+            if (sub8(x1, x1, x2)) add8(x1, x1, pl);
+        } else {
+            sub8(v, v, u);
+            if (sub8(x2, x2, x1)) add8(x2, x2, pl);
+        }
+    }
+    fp_t r, r3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.l[i] = x1[i];
+        r3.l[i] = P::r3(i);
+    }
+    return fp_mul_ni<P>(r, r3);
 }
 
 // 16-byte vector load/store of a field element (global or shared, 16-byte aligned)

@@ -47,6 +47,33 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fp_t* __restrict__ sca
     }
 }
 
+// Optimistic single pass: every bucket owns `cap` slots (mean size + 25 %), entries that do not fit are counted in
+// *dropped and the caller falls back to the exact two-pass counting sort (skewed scalars).
+__global__ void __launch_bounds__(256) k_msm_scatter_fixed(const fp_t* __restrict__ scalars, uint64_t n, uint32_t c, uint32_t W,
+                                                           uint32_t key_n, uint64_t first, uint32_t cap, uint32_t* __restrict__ cursor,
+                                                           uint32_t* __restrict__ entries, uint32_t* __restrict__ dropped) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_t k = fp_from_mont<S>(fp_load_ro(scalars + i));
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0, lost = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t v = scalar_bits(k.l, w * c, c) + carry;
+        uint32_t neg = v >= half && w + 1 < W ? 1u : 0u;
+        uint32_t mag = neg ? (1u << c) - v : v;
+        carry = neg;
+        if (mag) {
+            uint32_t b = mag - 1;
+            uint32_t pos = atomicAdd(cursor + b, 1u);
+            if (pos < cap)
+                entries[(size_t)b * cap + pos] = (uint32_t)((uint64_t)w * key_n + first + i) | (neg << 31);
+            else
+                ++lost;
+        }
+    }
+    if (lost) atomicAdd(dropped, lost);
+}
+
 // single-CTA exclusive scan of `n` counts (n <= 2^20), also zeroes the counts for their second life as cursors
 __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets) {
     __shared__ uint32_t sh[1024];
@@ -86,15 +113,20 @@ __device__ __forceinline__ xyzz_t shfl_xor_xyzz(const xyzz_t& v, int mask) {
 
 // P (power of two <= 32) adjacent lanes per bucket
 __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
-                                                    const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P,
+                                                    const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P, uint32_t cap,
                                                     xyzz_t* __restrict__ buckets) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = (uint32_t)(t / P), p = (uint32_t)(t % P);
     bool live = b < nb;
     uint32_t lo = 0, hi = 0;
     if (live) {
-        lo = offsets[b];
-        hi = offsets[b + 1];
+        if (cap) {  // fixed-capacity layout: offsets[] holds the bucket sizes
+            lo = b * cap;
+            hi = lo + offsets[b];
+        } else {
+            lo = offsets[b];
+            hi = offsets[b + 1];
+        }
     }
     xyzz_t acc = xyzz_inf();
     uint32_t i = lo + p, e = 0;
@@ -190,33 +222,63 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     const uint32_t nb = 1u << (k.c - 1);
     DevBuf<uint32_t> counts, offsets, entries;
     DevBuf<xyzz_t> buckets, partial;
-    VK_TRY(counts.alloc(ctx, nb));
-    VK_TRY(offsets.alloc(ctx, nb + 1));
-    VK_TRY(entries.alloc(ctx, (size_t)n * k.W));
-    VK_TRY(buckets.alloc(ctx, nb));
     cudaStream_t s = ctx->stream;
-    VK_CUDA(cudaMemsetAsync(counts, 0, nb * sizeof(uint32_t), s));
+    VK_TRY(counts.alloc(ctx, nb + 1));
+    VK_TRY(buckets.alloc(ctx, nb));
+    VK_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * sizeof(uint32_t), s));
     uint32_t gb = ceil_div_u64(n, 256);
-    if (n) {
-        k_msm_digits<false><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, nullptr, nullptr);
-        VK_TRY(launch_check(ctx));
-    }
-    k_scan<<<1, 1024, 0, s>>>(counts, nb, offsets);
-    VK_TRY(launch_check(ctx));
-    if (n) {
-        k_msm_digits<true><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, offsets, entries);
-        VK_TRY(launch_check(ctx));
-    }
-    // lanes per bucket: aim at ~24 additions per lane
+    // lanes per bucket: aim at ~32 additions per lane
     uint64_t avg = (uint64_t)n * k.W / nb;
     uint32_t P = 1;
-    while (P < 32 && avg / (P * 2) >= 16) P *= 2;
-    uint64_t threads = (uint64_t)nb * P;
-    {
-        KernelTimer timer(ctx);
-        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries, nb, P, buckets);
+    static int p_env = -1;
+    if (p_env < 0) {
+        const char* e = getenv("VKZG_MSM_P");
+        p_env = e ? atoi(e) : 0;
     }
-    VK_TRY(launch_check(ctx));
+    while (P < 32 && avg / (P * 2) >= 48) P *= 2;  // ~64 additions per lane (measured best on B200: P = 8 at n = 2^20)
+    if (p_env == 1 || p_env == 2 || p_env == 4 || p_env == 8 || p_env == 16 || p_env == 32) P = (uint32_t)p_env;
+    uint64_t threads = (uint64_t)nb * P;
+    bool done = false;
+    // ---- optimistic single pass (uniform scalars): fixed-capacity bucket lists, no count pass, no scan
+    uint64_t cap64 = avg + avg / 4 + 64;
+    if (n >= (1u << 12) && cap64 * nb < (1ull << 31) && !getenv("VKZG_MSM_TWO_PASS")) {
+        const uint32_t cap = (uint32_t)cap64;
+        VK_TRY(entries.alloc(ctx, (size_t)cap * nb));
+        k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, counts, entries, counts.p + nb);
+        VK_TRY(launch_check(ctx));
+        uint32_t dropped = 0;
+        VK_CUDA(cudaMemcpyAsync(&dropped, counts.p + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        VK_CUDA(cudaStreamSynchronize(s));
+        if (dropped == 0) {
+            KernelTimer timer(ctx);
+            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, buckets);
+            done = true;
+        } else {
+            VK_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * sizeof(uint32_t), s));
+        }
+        VK_TRY(launch_check(ctx));
+    }
+    if (!done) {
+        // ---- exact two-pass counting sort
+        DevBuf<uint32_t> entries2;
+        VK_TRY(offsets.alloc(ctx, nb + 1));
+        VK_TRY(entries2.alloc(ctx, (size_t)n * k.W));
+        if (n) {
+            k_msm_digits<false><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, nullptr, nullptr);
+            VK_TRY(launch_check(ctx));
+        }
+        k_scan<<<1, 1024, 0, s>>>(counts, nb, offsets);
+        VK_TRY(launch_check(ctx));
+        if (n) {
+            k_msm_digits<true><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, offsets, entries2);
+            VK_TRY(launch_check(ctx));
+        }
+        {
+            KernelTimer timer(ctx);
+            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets);
+        }
+        VK_TRY(launch_check(ctx));
+    }
     uint32_t segs = (nb + RED_SEG - 1) / RED_SEG;
     uint32_t rblocks = (segs + RED_THREADS - 1) / RED_THREADS;
     VK_TRY(partial.alloc(ctx, rblocks + 1));

@@ -204,9 +204,9 @@ using namespace vk;
 
 extern "C" {
 
-int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
-                              const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
-                              vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+static int32_t multiproof_prove_impl(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, bool f_on_device,
+                                     const vkzg_g1_affine* C, const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D,
+                                     vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
     VK_TRY(ctx_check(ctx));
     Key* k = ctx->key(key_id);
     if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
@@ -221,8 +221,12 @@ int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, co
     cudaStream_t s = ctx->stream;
 
     // rows to the device first (asynchronous for pinned memory), so the host hash below overlaps the copy
-    DevBuf<fp_t> df;
-    VK_TRY(upload(ctx, df, f, m * N));
+    DevBuf<fp_t> df_buf;
+    const fp_t* df = (const fp_t*)f;
+    if (!f_on_device) {
+        VK_TRY(upload(ctx, df_buf, f, m * N));
+        df = df_buf.p;
+    }
 
     // outer transcript: (C, z, y) per query -> r          multiproof.rs:108-115
     HostTranscript tr("multiproof");
@@ -327,6 +331,18 @@ int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, co
     }
     VK_TRY(download(ctx, yout, dyo.p, 1));
     return stream_sync(ctx);
+}
+
+int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
+                              const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
+                              vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+    return multiproof_prove_impl(ctx, key_id, scheme, f, false, C, z, y, m, D, L, R, tip, yout);
+}
+
+int32_t vkzg_multiproof_prove_dev(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* d_f, const vkzg_g1_affine* C,
+                                  const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
+                                  vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+    return multiproof_prove_impl(ctx, key_id, scheme, d_f, true, C, z, y, m, D, L, R, tip, yout);
 }
 
 int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* C, const uint64_t* z, const vkzg_fr* y,

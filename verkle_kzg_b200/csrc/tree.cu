@@ -50,7 +50,10 @@ int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint6
         k_tree_scalars<<<ceil_div_u64(n_terms, 128), 128, 0, ctx->stream>>>(d_child, d_lit, d_prev, n_terms, sc);
         VK_TRY(launch_check(ctx));
     }
-    VK_TRY(fixed_base_msm_csr(ctx, k, sc, 0, n_nodes, 0, 0xffffffffu, d_row_ptr, d_slot, acc));
+    // lanes per node by the level's mean number of terms (leaf-side levels have 2-3 terms, internal nodes up to 256)
+    uint64_t avg_terms = n_terms / n_nodes;
+    uint32_t lpj = avg_terms <= 4 ? 4 : (avg_terms <= 48 ? 8 : 32);
+    VK_TRY(fixed_base_msm_csr(ctx, k, sc, 0, n_nodes, 0, 0xffffffffu, d_row_ptr, d_slot, acc, lpj));
     return normalize_points(ctx, acc, n_nodes, d_out);
 }
 
