@@ -89,6 +89,13 @@ int32_t vkzg_g1_sum(vkzg_ctx* ctx, const vkzg_g1_affine* points, uint64_t n, vkz
 int32_t vkzg_to_data_item(vkzg_ctx* ctx, const vkzg_g1_affine* points, uint64_t n, vkzg_fr* out);
 int32_t vkzg_to_data_item_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_points, uint64_t n, vkzg_fr* d_out);
 
+/* ---- L1 / I2: element-wise Fr vector arithmetic — LagrangeBasis AddAssign / Sub / Mul<F> (lagrange_basis.rs:202-233),
+ *      utils::elementwise_mul and vec_add_and_distribute (utils.rs:21-38).
+ *      op: 0 a + b, 1 a - b, 2 a .* b, 3 a * x, 4 a + x * b.  `x` is a HOST pointer to one scalar (ops 3, 4).        */
+int32_t vkzg_fr_vector_op(vkzg_ctx* ctx, int32_t op, const vkzg_fr* a, const vkzg_fr* b, const vkzg_fr* x, uint64_t n, vkzg_fr* out);
+int32_t vkzg_fr_vector_op_dev(vkzg_ctx* ctx, int32_t op, const vkzg_fr* d_a, const vkzg_fr* d_b, const vkzg_fr* x, uint64_t n,
+                              vkzg_fr* d_out);
+
 /* ---- B1 / E1 / K1 / K2: precompute.rs:72-90, lagrange_basis.rs:63-83, :91-119, :121-142 ---------------- */
 /* barycentric coefficients of B points over the key's domain (size N): out[B][N] */
 int32_t vkzg_barycentric_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* points, uint64_t B, vkzg_fr* out);

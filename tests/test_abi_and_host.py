@@ -55,6 +55,32 @@ def test_product_does_not_import_the_oracle():
                 assert "liborc" not in src and "import orc" not in src and "oracle/" not in src, f
 
 
+def test_host_transcript_helpers(vk):
+    """host_hash.cpp (outer multiproof transcript): SHA-256 against hashlib at every padding boundary, and the
+    native-limb serialisation against the oracle's ark-serialize restatement"""
+    import hashlib
+    lib = vk._lib.lib()
+    rng = np.random.default_rng(1)
+    for n in [0, 1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 1000, 300000]:
+        msg = rng.bytes(n)
+        out = (ctypes.c_uint8 * 32)()
+        lib.vkh_sha256(msg, ctypes.c_size_t(n), out)
+        assert bytes(out) == hashlib.sha256(msg).digest(), n
+    k0, k1 = orc.rand_fr(rng, 2)
+    pts = np.concatenate([orc.points_walk(k0, k1, 40), np.zeros((1, 64), dtype=np.uint8)])
+    exp = orc.g1_compress(pts)
+    for i in range(len(pts)):
+        out = (ctypes.c_uint8 * 32)()
+        lib.vkh_serialize_g1(pts[i].ctypes.data_as(ctypes.c_void_p), out)
+        assert bytes(out) == bytes(exp[i])
+    xs = orc.rand_fr(rng, 20) + [0, 1, orc.R_MOD - 1]
+    buf = orc.fr_to_buf(xs)
+    for i, x in enumerate(xs):
+        out = (ctypes.c_uint8 * 32)()
+        lib.vkh_serialize_fr(buf[i].ctypes.data_as(ctypes.c_void_p), out)
+        assert int.from_bytes(bytes(out), "little") == x
+
+
 def _oracle_eval_levels(bases, levels):
     """commit every node of the flattened tree with the oracle (CPU), leaves first"""
     nodes = []

@@ -114,3 +114,18 @@ def test_open_batch_property_full_width(eng):
     for i in range(0, B, 9):
         assert orc.kzg_verify_tau(srs, TAU, C[i], zb[i], proof[i], y[i])
     key.free()
+
+
+def test_fr_vector_ops(eng):
+    """L1 / I2: LagrangeBasis AddAssign / Sub / Mul<F>, elementwise_mul, vec_add_and_distribute"""
+    rng = np.random.default_rng(21)
+    n = 1000
+    a, b = orc.rand_fr_buf(rng, n), orc.rand_fr_buf(rng, n)
+    a[0], b[0] = orc.fr_to_buf([orc.R_MOD - 1])[0], orc.fr_to_buf([orc.R_MOD - 1])[0]
+    x = orc.rand_fr_buf(rng, 1)[0]
+    xs = np.tile(x, (n, 1))
+    assert (eng.fr_vector_op("add", a, b) == orc.field_op(0, "add", a, b)).all()
+    assert (eng.fr_vector_op("sub", a, b) == orc.field_op(0, "sub", a, b)).all()
+    assert (eng.fr_vector_op("mul", a, b) == orc.field_op(0, "mul", a, b)).all()
+    assert (eng.fr_vector_op("scale", a, x=x) == orc.field_op(0, "mul", a, xs)).all()
+    assert (eng.fr_vector_op("axpy", a, b, x) == orc.field_op(0, "add", a, orc.field_op(0, "mul", b, xs))).all()

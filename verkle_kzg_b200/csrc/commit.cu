@@ -68,7 +68,7 @@ template <int LPJ>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     k_fixed_base_msm(const affine_t* __restrict__ table, uint32_t c, uint32_t W, const fp_t* __restrict__ scalars, uint32_t T,
                      uint64_t jobs, uint32_t ipa_m, uint32_t q_row, const uint32_t* __restrict__ row_ptr,
-                     const uint16_t* __restrict__ slot, xyzz_t* __restrict__ out) {
+                     const uint16_t* __restrict__ slot, uint32_t split, xyzz_t* __restrict__ out) {
     extern __shared__ uint32_t smem[];
     constexpr uint32_t JPW = 32 / LPJ;                 // jobs per warp
     constexpr uint32_t CHUNK = CHUNK_TERMS / JPW;      // terms recoded per pass and group
@@ -77,12 +77,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     const uint32_t list_cap = CHUNK * W;
     uint32_t* list = smem + warp * (CHUNK_TERMS * W + 32) + grp * list_cap;
     uint32_t* cnt = smem + warp * (CHUNK_TERMS * W + 32) + CHUNK_TERMS * W + grp;
-    uint64_t job = ((uint64_t)blockIdx.x * WARPS_PER_CTA + warp) * JPW + grp;
-    const bool live = job < jobs;
+    // split > 1 (few wide jobs, e.g. a single proof): `jobs` counts SLICES, slice v covers the terms
+    // [s * Tsub, (s + 1) * Tsub) of job v / split and writes a partial sum (k_sum_slices adds them up)
+    const uint64_t vjob = ((uint64_t)blockIdx.x * WARPS_PER_CTA + warp) * JPW + grp;
+    const bool live = vjob < jobs;
+    uint64_t job = vjob;
+    uint32_t term0 = 0;
+    if (split > 1) {
+        job = vjob / split;
+        uint32_t Tsub = (T + split - 1) / split;
+        term0 = (uint32_t)(vjob % split) * Tsub;
+    }
+    const uint32_t Tfull = T;
     // dense: job j owns scalars[j*T .. (j+1)*T), term t uses base t.  CSR (row_ptr != nullptr, verkle nodes):
     // job j owns terms [row_ptr[j], row_ptr[j+1]) and term t uses base slot[t].
     const fp_t* sc = scalars + job * T;
     const uint16_t* sl = nullptr;
+    if (split > 1) {
+        uint32_t Tsub = (T + split - 1) / split;
+        T = term0 >= T ? 0 : (T - term0 < Tsub ? T - term0 : Tsub);  // terms of this slice
+        sc += term0;
+    }
     if (!live) T = 0;
     if (row_ptr && live) {
         uint32_t t0 = row_ptr[job];
@@ -109,8 +124,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
             uint32_t term = chunk + j;
             if (term < T) {
                 fp_t k = fp_from_mont<S>(fp_load_ro(sc + term));
-                uint32_t base = sl ? (uint32_t)sl[term] : term;
-                if (ipa_m) base = (term == T - 1 && q_row != 0xffffffffu) ? q_row : (term / ipa_m) * 2 * ipa_m + side_off + term % ipa_m;
+                uint32_t gt = term0 + term;  // term index within the whole job
+                uint32_t base = sl ? (uint32_t)sl[term] : gt;
+                if (ipa_m) base = (gt == Tfull - 1 && q_row != 0xffffffffu) ? q_row : (gt / ipa_m) * 2 * ipa_m + side_off + gt % ipa_m;
                 emit_entries(k, base * W, c, W, list, cnt);
             }
         }
@@ -144,16 +160,31 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
         acc = xyzz_add_ni(acc, o);
     }
     if (gl == 0 && live) {
-        fp_store(&out[job].x, acc.x);
-        fp_store(&out[job].y, acc.y);
-        fp_store(&out[job].zz, acc.zz);
-        fp_store(&out[job].zzz, acc.zzz);
+        fp_store(&out[vjob].x, acc.x);
+        fp_store(&out[vjob].y, acc.y);
+        fp_store(&out[vjob].zz, acc.zz);
+        fp_store(&out[vjob].zzz, acc.zzz);
     }
+}
+
+// out[j] = sum of the `split` slice sums of job j (one warp per job, shuffle tree)
+__global__ void __launch_bounds__(128) k_sum_slices(const xyzz_t* __restrict__ part, uint64_t jobs, uint32_t split, xyzz_t* __restrict__ out) {
+    uint64_t job = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (job >= jobs) return;
+    xyzz_t acc = xyzz_inf();
+    for (uint32_t s = lane; s < split; s += 32) acc = xyzz_add_ni(acc, part[job * split + s]);
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        xyzz_t o = shfl_xor_xyzz_c(acc, off);
+        acc = xyzz_add_ni(acc, o);
+    }
+    if (lane == 0) out[job] = acc;
 }
 
 template <int LPJ>
 static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
-                                 uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out) {
+                                 uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, uint32_t split, xyzz_t* d_out) {
     static bool attr_set = false;
     if (!attr_set) {
         VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm<LPJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -166,7 +197,7 @@ static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scal
     if (blocks > 0x7fffffffull) return VKZG_ERR_RANGE;
     KernelTimer timer(ctx);
     k_fixed_base_msm<LPJ><<<(uint32_t)blocks, WARPS_PER_CTA * 32, smem, ctx->stream>>>(k.table, k.c, k.W, d_scalars, T, jobs, ipa_m, q_row,
-                                                                                       d_row_ptr, d_slot, d_out);
+                                                                                       d_row_ptr, d_slot, split, d_out);
     return launch_check(ctx);
 }
 
@@ -174,9 +205,23 @@ static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scal
 int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                            uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job) {
     if (jobs == 0) return VKZG_OK;
-    if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, d_out);
-    if (lanes_per_job == 8) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, d_out);
-    return launch_fixed_base<32>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, d_out);
+    if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
+    if (lanes_per_job == 8) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
+    // few wide dense jobs (single proofs / commits): slice every job over several warps so the whole GPU works on it
+    if (!d_row_ptr && T >= 16 && jobs * 8 <= (uint64_t)ctx->sm_count * 16) {
+        uint32_t split = (T + 7) / 8;  // ~8 terms (128 table additions) per warp
+        uint64_t room = (uint64_t)ctx->sm_count * 16 / jobs;
+        if (split > room) split = (uint32_t)room;
+        if (split > 64) split = 64;
+        if (split > 1) {
+            DevBuf<xyzz_t> part;
+            VK_TRY(part.alloc(ctx, jobs * split));
+            VK_TRY(launch_fixed_base<32>(ctx, k, d_scalars, T, jobs * split, ipa_m, q_row, nullptr, nullptr, split, part));
+            k_sum_slices<<<ceil_div_u64(jobs * 32, 128), 128, 0, ctx->stream>>>(part, jobs, split, d_out);
+            return launch_check(ctx);
+        }
+    }
+    return launch_fixed_base<32>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
 }
 
 int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,

@@ -17,7 +17,8 @@ struct sha256_ctx {
 
 VK_HD uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
-__host__ __device__ inline void sha256_compress(uint32_t h[8], const uint8_t* blk) {
+// out of line: the fully unrolled 64 rounds are ~4 KB of code and the transcript kernels call it from many sites
+__host__ __device__ __noinline__ inline void sha256_compress(uint32_t h[8], const uint8_t* blk) {
     const uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
         0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,

@@ -15,8 +15,14 @@
 
 namespace vk {
 
-// ---- host side of the outer transcript (hash.cuh is host/device code) ----------------------------------
-struct HostTranscript {
+// ---- host side of the outer transcript (host_hash.cpp: SHA-NI / portable SHA-256, native-limb serialisation) ----
+extern "C" {
+void vkh_sha256(const uint8_t* data, size_t len, uint8_t out[32]);
+void vkh_serialize_fr(const uint64_t mont[4], uint8_t out[32]);
+void vkh_serialize_g1(const uint64_t xy_mont[8], uint8_t out[32]);
+}
+
+struct HostTranscript {  // TranscriptHasher (transcript.rs:28-62): byte-string state, digest = hash_to_field(state, 1)[0]
     std::vector<uint8_t> state;
     uint8_t dst[TR_DST_MAX];
     uint32_t dst_len;
@@ -32,13 +38,13 @@ struct HostTranscript {
     void append_point(const affine_t& p, const char* l) {
         uint8_t b[32];
         append_label(l);
-        affine_serialize(p, b);
+        vkh_serialize_g1((const uint64_t*)&p, b);
         append_raw(b, 32);
     }
     void append_fr(const fp_t& x, const char* l) {
         uint8_t b[32];
         append_label(l);
-        fr_serialize(x, b);
+        vkh_serialize_fr((const uint64_t*)&x, b);
         append_raw(b, 32);
     }
     void append_u64(uint64_t v, const char* l) {  // usize -> u64 little-endian (quirk Q5)
@@ -47,11 +53,31 @@ struct HostTranscript {
         append_label(l);
         append_raw(b, 8);
     }
+    // expand_message_xmd (RFC 9380) as ark-ff 0.4 drives it: Z_pad = 48 zero bytes, 48 output bytes (hash.cuh has the
+    // same construction for the device; the bulk hash b0 goes through the fast host SHA-256 here)
     fp_t digest(const char* l) {
         append_label(l);
-        fp_t res = hash_to_fr(state.data(), (uint32_t)state.size(), dst, dst_len);
+        std::vector<uint8_t> m(ARK04_Z_PAD_LEN, 0);
+        m.insert(m.end(), state.begin(), state.end());
+        const uint8_t lib[3] = {0, 48, 0};
+        m.insert(m.end(), lib, lib + 3);
+        m.insert(m.end(), dst, dst + dst_len);
+        m.push_back((uint8_t)dst_len);
+        uint8_t b0[32], b1[32], b2[32], u[48], t[32 + 1 + TR_DST_MAX + 1];
+        vkh_sha256(m.data(), m.size(), b0);
+        memcpy(t, b0, 32);
+        t[32] = 1;
+        memcpy(t + 33, dst, dst_len);
+        t[33 + dst_len] = (uint8_t)dst_len;
+        vkh_sha256(t, 34 + dst_len, b1);
+        for (int i = 0; i < 32; ++i) t[i] = b0[i] ^ b1[i];
+        t[32] = 2;
+        vkh_sha256(t, 34 + dst_len, b2);
+        memcpy(u, b1, 32);
+        memcpy(u + 32, b2, 16);
+        fp_t res = fr_from_be48(u);
         uint8_t b[32];
-        fr_serialize(res, b);
+        vkh_serialize_fr((const uint64_t*)&res, b);
         state.assign(b, b + 32);
         append_label(l);
         return res;

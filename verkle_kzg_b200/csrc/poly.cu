@@ -225,11 +225,53 @@ int32_t kzg_open_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len
     return normalize_points(ctx, acc, B, d_proof);
 }
 
+// L1 / I2: element-wise Fr vector arithmetic (lagrange_basis.rs:202-233 AddAssign / Sub / Mul<F>, utils.rs:21-38
+// elementwise_mul / vec_add_and_distribute).  Pure streaming: 64-96 bytes moved per 0-1 multiplication, HBM-bound.
+__global__ void __launch_bounds__(256) k_fr_vec(int op, const fp_t* __restrict__ a, const fp_t* __restrict__ b, fp_t x, uint64_t n,
+                                                fp_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_t va = fp_load_ro(a + i), r;
+    switch (op) {
+        case 0: r = fp_add<S>(va, fp_load_ro(b + i)); break;                       // a + b
+        case 1: r = fp_sub<S>(va, fp_load_ro(b + i)); break;                       // a - b
+        case 2: r = fp_mul<S>(va, fp_load_ro(b + i)); break;                       // a .* b
+        case 3: r = fp_mul<S>(va, x); break;                                       // a * x
+        default: r = fp_add<S>(va, fp_mul<S>(x, fp_load_ro(b + i))); break;        // a + x * b
+    }
+    fp_store(out + i, r);
+}
+
 }  // namespace vk
 
 using namespace vk;
 
 extern "C" {
+
+int32_t vkzg_fr_vector_op_dev(vkzg_ctx* ctx, int32_t op, const vkzg_fr* d_a, const vkzg_fr* d_b, const vkzg_fr* x, uint64_t n,
+                              vkzg_fr* d_out) {
+    VK_TRY(ctx_check(ctx));
+    if (op < 0 || op > 4 || (n && (!d_a || !d_out))) return VKZG_ERR_ARG;
+    if (n && op != 3 && !d_b) return VKZG_ERR_ARG;
+    if ((op == 3 || op == 4) && !x) return VKZG_ERR_ARG;
+    if (!n) return VKZG_OK;
+    fp_t xv = fp_zero<S>();
+    if (x) memcpy(&xv, x, sizeof(xv));
+    k_fr_vec<<<ceil_div_u64(n, 256), 256, 0, ctx->stream>>>(op, (const fp_t*)d_a, (const fp_t*)(d_b ? d_b : d_a), xv, n, (fp_t*)d_out);
+    return launch_check(ctx);
+}
+
+int32_t vkzg_fr_vector_op(vkzg_ctx* ctx, int32_t op, const vkzg_fr* a, const vkzg_fr* b, const vkzg_fr* x, uint64_t n, vkzg_fr* out) {
+    VK_TRY(ctx_check(ctx));
+    if (n && (!a || !out)) return VKZG_ERR_ARG;
+    DevBuf<fp_t> da, db, dout;
+    VK_TRY(upload(ctx, da, a, n));
+    if (b) VK_TRY(upload(ctx, db, b, n));
+    VK_TRY(dout.alloc(ctx, n));
+    VK_TRY(vkzg_fr_vector_op_dev(ctx, op, (const vkzg_fr*)da.p, b ? (const vkzg_fr*)db.p : nullptr, x, n, (vkzg_fr*)dout.p));
+    VK_TRY(download(ctx, out, dout.p, n));
+    return stream_sync(ctx);
+}
 
 int32_t vkzg_evaluate_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n, const vkzg_fr* points,
                             uint64_t B, vkzg_fr* out) {

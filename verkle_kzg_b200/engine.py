@@ -128,6 +128,23 @@ class Engine:
         check(self._L.vkzg_to_data_item(self._ctx, hptr(p), ctypes.c_uint64(len(p)), hptr(out)), "vkzg_to_data_item")
         return out
 
+    # ---------------------------------------------------------------- L1 / I2
+    _VEC_OPS = {"add": 0, "sub": 1, "mul": 2, "scale": 3, "axpy": 4}
+
+    def fr_vector_op(self, op, a, b=None, x=None):
+        a = u8(a, 32).reshape(-1, 32)
+        bb = None if b is None else u8(b, 32).reshape(-1, 32)
+        xx = None if x is None else u8(x, 32).reshape(32)
+        out = np.zeros_like(a)
+        check(self._L.vkzg_fr_vector_op(self._ctx, ctypes.c_int32(self._VEC_OPS[op]), hptr(a), hptr(bb), hptr(xx), ctypes.c_uint64(len(a)),
+                                        hptr(out)), "vkzg_fr_vector_op")
+        return out
+
+    def fr_vector_op_dev(self, op, d_a, d_b, x, n, d_out):
+        xx = None if x is None else u8(x, 32).reshape(32)
+        check(self._L.vkzg_fr_vector_op_dev(self._ctx, ctypes.c_int32(self._VEC_OPS[op]), dptr(d_a), dptr(d_b), hptr(xx), ctypes.c_uint64(n),
+                                            dptr(d_out)), "vkzg_fr_vector_op_dev")
+
     # ---------------------------------------------------------------- B1
     def barycentric_batch(self, key, points):
         pts = u8(points, 32).reshape(-1, 32)
