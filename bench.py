@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (default: BASELINE config size)")
     ap.add_argument("--log2n", type=int, default=20, help="msm: log2 of the number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window-bits", type=int, default=0, help="fixed-base window width c of the width-256 key (default 16; up to 20)")
     return ap.parse_args()
 
 
@@ -283,8 +284,25 @@ def hp(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def window_table_bytes(c, nbases):
+    return nbases * ((256 + c - 1) // c) * (1 << (c - 1)) * 64
+
+
+def pick_window_bits(torch, nbases):
+    """largest fixed-base window width whose tables fit this GPU's FREE memory with room for the batch (the tables are the
+    memory-for-work knob of the design: 13 table additions per scalar at c = 20 / 112 GB, 16 at c = 16 / 8.6 GB)"""
+    free, _ = torch.cuda.mem_get_info()
+    for c in (20, 19, 18, 16):
+        if window_table_bytes(c, nbases) + (12 << 30) <= free:
+            return c
+    return 16
+
+
 def run_native(args):
+    global WINDOW_BITS, WINDOWS
     torch, dist, world, rank, local = dist_setup(args)
+    WINDOW_BITS = args.window_bits or pick_window_bits(torch, N_WIDTH + 1)
+    WINDOWS = (256 + WINDOW_BITS - 1) // WINDOW_BITS
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: verkle_kzg_b200 has no CPU path")
     from verkle_kzg_b200 import Engine, _lib
@@ -301,7 +319,9 @@ def run_native(args):
     if wl in ("ipa", "commit", "kzg"):
         B = args.batch or (1 << 14)
         bases = make_points_dev(torch, eng, N_WIDTH + 1, gen)
+        t_key = time.perf_counter()
         key = eng.load_key_dev(bases, N_WIDTH, d_q=bases[N_WIDTH:] if wl == "ipa" else None, window_bits=WINDOW_BITS)
+        extra["key_load_s"] = round(time.perf_counter() - t_key, 2)
         gen.manual_seed(0x5EED1000 + rank)
         a = rand_fr_dev(torch, B * N_WIDTH, gen).reshape(B, N_WIDTH, 32)
         zi = torch.randint(0, N_WIDTH, (B,), device="cuda", generator=gen)
@@ -393,7 +413,7 @@ def run_native(args):
                 dist.all_gather_into_tensor(allp, part)
                 eng.g1_sum_dev(allp, world, out)
                 out_h.copy_(out)
-        madds_per_unit = WINDOWS
+        madds_per_unit = 16                                                      # MSM keys: c = 16 -> 16 signed digits per scalar
         launches_timed = 1
         units_per_step = per
         h2d, d2h = s_h.numel(), 64
@@ -486,7 +506,11 @@ def run_native(args):
     else:
         raise SystemExit(f"unknown workload {wl}")
 
-    cfg["l2_policy"] = "inputs and tables exceed the 126 MB L2 (window tables 8.6 GB, scalars >= 128 MB); no flush needed"
+    cfg.update(extra)
+    if wl != "msm":
+        cfg["window_bits"] = WINDOW_BITS
+        cfg["window_table_gb"] = round(key.table_bytes / 1e9, 1)
+    cfg["l2_policy"] = "tables (GBs) and inputs (>= 128 MB) exceed the 126 MB L2; no flush needed"
     # ---- device-resident timing, with the dominant kernel bracketed by its own event pairs
     for _ in range(args.warmup):
         step()

@@ -123,7 +123,7 @@ int32_t vkzg_key_load_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_bases, uint32_t
     if (kind == VKZG_KEY_MSM && d_q) return VKZG_ERR_ARG;
     uint32_t c = window_bits;
     if (c == 0) c = kind == VKZG_KEY_WINDOW ? 16 : (n >= (1u << 14) ? 16 : 12);
-    if (c < 2 || c > 20 || (kind == VKZG_KEY_WINDOW && c > 16)) return VKZG_ERR_ARG;
+    if (c < 2 || c > 20) return VKZG_ERR_ARG;
     k.c = c;
     k.W = (256 + c - 1) / c;
     uint32_t nb = n + (k.has_q ? 1 : 0);
