@@ -130,6 +130,9 @@ def dist_setup(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # NCCL prints a version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -490,8 +493,15 @@ def run_native(args):
                 dist.all_gather_into_tensor(allp, nodes[total_nodes - 1:total_nodes])
                 eng.g1_sum_dev(allp, world, root)
 
+        from verkle_kzg_b200.tree import NativeVerkleTree
+        kk, vv = keys_all[sel], vals_all[sel]
+
         def step_e2e():
-            eng.tree_commit_levels(key, levels)
+            # configs[4] end to end: bulk insert into the native host tree (libvkzg, Node::insert semantics) + recommit to the root
+            t = NativeVerkleTree(32, 256)
+            t.insert_many(kk, vv)
+            t.commitment(eng, key)
+            t.close()
         terms = sum(len(lv["slot"]) for lv in levels)
         madds_per_unit = terms * WINDOWS / max(1, int(sel.sum()))               # upper bound: zero digits are skipped at run time
         launches_timed = len(levels)

@@ -171,6 +171,31 @@ int32_t vkzg_tree_commit_levels(vkzg_ctx* ctx, uint32_t key_id, uint32_t n_level
                                 const uint32_t* const* row_ptr, const uint16_t* const* slot, const int32_t* const* child,
                                 const vkzg_fr* const* lit, vkzg_g1_affine* root_out);
 
+/* ---- next row: the verkle tree's host structure, VerkleTree::{new, insert_single, get_single, commitment}
+ *      (verkle-tree/src/lib.rs:106-137) with Node::insert (node.rs:133-197) mirrored literally (Unit = u8).  Node
+ *      commitments are cached and cleared along insertion paths like the reference; vkzg_tree_commit recommits only the
+ *      dirty nodes, level by level.  ext_width = the reference's const generic N of the extension layout (quirk Q6), 256 for
+ *      the Ethereum layout.  The key must have >= max(256, ext_width) bases.                                             */
+typedef struct vkzg_tree vkzg_tree;
+int32_t vkzg_tree_create(vkzg_tree** out, uint32_t key_len, uint32_t ext_width);
+int32_t vkzg_tree_destroy(vkzg_tree* tree);
+/* n (key, 32-byte value) pairs inserted IN ORDER; VKZG_ERR_RANGE at the first pair the reference panics on ("Traversed to
+ * extension node with differing stem"), *n_done = pairs inserted before it                                               */
+int32_t vkzg_tree_insert(vkzg_tree* tree, const uint8_t* keys, const uint8_t* values, uint64_t n, uint64_t* n_done);
+/* 1 = found (value copied to value_out[32]), 0 = absent */
+int32_t vkzg_tree_get(const vkzg_tree* tree, const uint8_t* key, uint8_t* value_out);
+uint64_t vkzg_tree_nodes(const vkzg_tree* tree);
+int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* tree, vkzg_g1_affine* root_out, uint64_t* n_committed);
+
+/* ---- next row: KZG::setup (kzg/mod.rs:115-124) -------------------------------------------------------- */
+/* powers[m] = [tau^i]G  ->  lagrange[n], n = next_pow2(m): the group inverse FFT over the radix-2 domain of size n
+ * (`domain.ifft(&g1_points)`, inputs beyond m are the identity).                                                  */
+int32_t vkzg_kzg_setup(vkzg_ctx* ctx, const vkzg_g1_affine* powers, uint32_t m, vkzg_g1_affine* lagrange);
+int32_t vkzg_kzg_setup_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_powers, uint32_t m, vkzg_g1_affine* d_lagrange);
+/* KZGRandomPointGenerator::gen (kzg_point_generator.rs:32-43): out[i] = tau^i * G, i < m; key_id = a window key whose
+ * base 0 is the generator G                                                                                       */
+int32_t vkzg_kzg_powers(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* tau, uint32_t m, vkzg_g1_affine* out);
+
 /* ---- measurement helpers (tools/, bench.py) ------------------------------------------------------------ */
 /* enable != 0: bracket every launch of the dominant kernel (k_fixed_base_msm for window keys, k_msm_bucket for
  * MSM keys) with a CUDA event pair on the context's stream; calling it again clears the record.            */

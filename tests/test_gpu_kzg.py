@@ -129,3 +129,21 @@ def test_fr_vector_ops(eng):
     assert (eng.fr_vector_op("mul", a, b) == orc.field_op(0, "mul", a, b)).all()
     assert (eng.fr_vector_op("scale", a, x=x) == orc.field_op(0, "mul", a, xs)).all()
     assert (eng.fr_vector_op("axpy", a, b, x) == orc.field_op(0, "add", a, orc.field_op(0, "mul", b, xs))).all()
+
+
+@pytest.mark.parametrize("m", [1, 5, 16, 20, 256])
+def test_kzg_setup_group_ifft(eng, m):
+    """KZG::setup (kzg/mod.rs:115-124): powers of tau -> Lagrange SRS, against the oracle's scalar-side construction"""
+    gen = orc.g1_generator()
+    gkey = eng.load_key(gen.reshape(1, 64), window_bits=8)
+    tau = orc.fr_to_buf([TAU])[0]
+    powers = eng.kzg_powers(gkey, tau, m)
+    exp_pow = orc.g1_mul_gen_batch(orc.fr_to_buf([pow(TAU, i, orc.R_MOD) for i in range(m)]))
+    assert (powers == exp_pow).all()
+    got = eng.kzg_setup(powers)
+    assert (got == orc.kzg_setup(m, TAU)).all()
+    # a random secret as well
+    t2 = orc.rand_fr(np.random.default_rng(m), 1)[0]
+    p2 = orc.g1_mul_gen_batch(orc.fr_to_buf([pow(t2, i, orc.R_MOD) for i in range(m)]))
+    assert (eng.kzg_setup(p2) == orc.kzg_setup(m, t2)).all()
+    gkey.free()

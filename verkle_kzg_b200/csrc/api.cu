@@ -72,6 +72,7 @@ int32_t vkzg_ctx_destroy(vkzg_ctx* ctx) {
         cudaFree(kv.second.dom.omega);
     }
     for (auto& kv : ctx->domains) cudaFree(kv.second.omega);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VKZG_OK;
@@ -219,11 +220,27 @@ int32_t vkzg_commit_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_s
 int32_t vkzg_commit_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* scalars, uint32_t w, uint64_t B, vkzg_g1_affine* out) {
     VK_TRY(ctx_check(ctx));
     if (B && (!scalars || !out)) return VKZG_ERR_ARG;
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
+    if (w == 0 || w > k->n) return VKZG_ERR_RANGE;
+    if (B == 0) return VKZG_OK;
     DevBuf<fp_t> ds;
     DevBuf<affine_t> dout;
-    VK_TRY(upload(ctx, ds, scalars, (size_t)B * w));
+    DevBuf<xyzz_t> acc;
+    VK_TRY(ds.alloc(ctx, (size_t)B * w));
     VK_TRY(dout.alloc(ctx, B));
-    VK_TRY(vkzg_commit_batch_dev(ctx, key_id, (const vkzg_fr*)ds.p, w, B, (vkzg_g1_affine*)dout.p));
+    VK_TRY(acc.alloc(ctx, B));
+    // chunks of the batch upload on the copy stream while the previous chunk is committed
+    ChunkedUpload up(ctx);
+    VK_TRY(up.init());
+    const uint64_t chunk = pipeline_chunk(B);
+    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
+        uint64_t nb = B - b0 < chunk ? B - b0 : chunk;
+        VK_TRY(up.copy(ds.p + b0 * w, (const fp_t*)scalars + b0 * w, nb * w * sizeof(fp_t)));
+        VK_TRY(up.publish());
+        VK_TRY(fixed_base_msm(ctx, *k, ds.p + b0 * w, w, nb, 0, 0xffffffffu, acc.p + b0));
+    }
+    VK_TRY(normalize_points(ctx, acc, B, dout));
     VK_TRY(download(ctx, out, dout.p, B));
     return stream_sync(ctx);
 }

@@ -121,9 +121,83 @@ const uint64_t FR_INV = 0xc2e1f593efffffffULL;  // -r^-1 mod 2^64
 const uint64_t FQ_INV = 0x87d20782e4866389ULL;  // -p^-1 mod 2^64
 const uint64_t FQ_HALF[4] = {0x9e10460b6c3e7ea3ULL, 0xcbc0b548b438e546ULL, 0xdc2822db40c0ac2eULL, 0x183227397098d014ULL};  // (p-1)/2
 
+// 4 x 64-bit limb Montgomery product a * b * R^-1 mod r (CIOS); a may be any 256-bit value, b < r
+void montmul_fr(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        unsigned __int128 c = 0;
+        for (int j = 0; j < 4; ++j) {
+            c += (unsigned __int128)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FR_INV;
+        c = (unsigned __int128)m * FR_P[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; ++j) {
+            c += (unsigned __int128)m * FR_P[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    uint64_t d[4];
+    unsigned __int128 bw = 0;
+    for (int i = 0; i < 4; ++i) {
+        unsigned __int128 x = (unsigned __int128)t[i] - FR_P[i] - (uint64_t)bw;
+        d[i] = (uint64_t)x;
+        bw = (x >> 64) & 1;
+    }
+    bool ge = t[4] != 0 || bw == 0;
+    for (int i = 0; i < 4; ++i) out[i] = ge ? d[i] : t[i];
+}
+
+const uint64_t FR_R2[4] = {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL};  // R^2 mod r
+
 }  // namespace
 
 extern "C" {
+
+// F::from_le_bytes_mod_order(bytes) in Montgomery form (the literals of verkle nodes: 16-byte value halves, stems)
+void vkh_fr_from_le_bytes(const uint8_t* b, size_t len, uint64_t out[4]) {
+    // Horner over 31-byte digits (each < 2^248 < r), most significant first: acc = acc * 2^248 + digit
+    uint64_t acc[4] = {0, 0, 0, 0};
+    uint64_t radix[4] = {0, 0, 0, 1ULL << 56}, radix_m[4];
+    montmul_fr(radix, FR_R2, radix_m);  // 2^248 in Montgomery form
+    size_t digits = (len + 30) / 31;
+    for (size_t d = digits; d-- > 0;) {
+        size_t lo = d * 31, n = len - lo < 31 ? len - lo : 31;
+        uint8_t tmp[32] = {0};
+        memcpy(tmp, b + lo, n);
+        uint64_t v[4], vm[4];
+        memcpy(v, tmp, 32);
+        montmul_fr(v, FR_R2, vm);
+        if (d + 1 < digits) montmul_fr(acc, radix_m, acc);
+        // acc += vm (mod r)
+        unsigned __int128 c = 0;
+        uint64_t s[4];
+        for (int i = 0; i < 4; ++i) {
+            c += (unsigned __int128)acc[i] + vm[i];
+            s[i] = (uint64_t)c;
+            c >>= 64;
+        }
+        uint64_t dd[4];
+        unsigned __int128 bw = 0;
+        for (int i = 0; i < 4; ++i) {
+            unsigned __int128 x = (unsigned __int128)s[i] - FR_P[i] - (uint64_t)bw;
+            dd[i] = (uint64_t)x;
+            bw = (x >> 64) & 1;
+        }
+        bool ge = c != 0 || bw == 0;
+        for (int i = 0; i < 4; ++i) acc[i] = ge ? dd[i] : s[i];
+    }
+    memcpy(out, acc, 32);
+}
 
 // one-shot SHA-256 of a contiguous buffer
 void vkh_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {

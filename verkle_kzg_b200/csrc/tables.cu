@@ -247,6 +247,18 @@ int32_t build_domain(vkzg_ctx* ctx, uint32_t log2n, uint32_t size_n, DomainTable
     return VKZG_OK;
 }
 
+// cached constants of the radix-2 domain of size 2^lg
+int32_t domain_for(vkzg_ctx* ctx, uint32_t lg, const DomainTables*& dt) {
+    auto it = ctx->domains.find(lg);
+    if (it == ctx->domains.end()) {
+        DomainTables d;
+        VK_TRY(build_domain(ctx, lg, 1u << lg, d));
+        it = ctx->domains.emplace(lg, d).first;
+    }
+    dt = &it->second;
+    return VKZG_OK;
+}
+
 int32_t build_domain_tables(vkzg_ctx* ctx, Key& k) {
     uint32_t lg = 0;
     while ((1u << lg) < k.n) ++lg;

@@ -69,6 +69,7 @@ struct vkzg_ctx {
     std::map<uint32_t, vk::Key> keys;
     // optional per-kernel timing of the dominant kernel (bench.py's roofline): CUDA event pairs around
     // every k_fixed_base_msm / k_msm_bucket launch on this context's stream
+    cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     uint64_t timing_units = 0;  // point additions issued by the timed launches (upper bound: zero digits excluded at run time)
@@ -155,6 +156,49 @@ static inline int32_t stream_sync(vkzg_ctx* ctx) {
     return VKZG_OK;
 }
 
+// Chunked upload for the batched host-pointer entry points: the rows of chunk i + 1 cross PCIe on the copy stream
+// while chunk i computes on the main stream (pinned host memory; pageable memory degrades to synchronous staging).
+struct ChunkedUpload {
+    vkzg_ctx* ctx;
+    std::vector<cudaEvent_t> evs;
+    explicit ChunkedUpload(vkzg_ctx* c) : ctx(c) {}
+    ~ChunkedUpload() {
+        for (auto e : evs) cudaEventDestroy(e);
+    }
+    int32_t init() {
+        if (!ctx->copy_stream) VK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        // the destination buffers were allocated in main-stream order: the copy stream must not run ahead of that
+        cudaEvent_t e;
+        VK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+        VK_CUDA(cudaEventRecord(e, ctx->stream));
+        VK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, e, 0));
+        return VKZG_OK;
+    }
+    // enqueue dst <- src on the copy stream
+    int32_t copy(void* dst, const void* src, size_t bytes) {
+        if (bytes) VK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        return VKZG_OK;
+    }
+    // main stream waits for everything enqueued on the copy stream so far
+    int32_t publish() {
+        cudaEvent_t e;
+        VK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+        VK_CUDA(cudaEventRecord(e, ctx->copy_stream));
+        VK_CUDA(cudaStreamWaitEvent(ctx->stream, e, 0));
+        return VKZG_OK;
+    }
+};
+
+// chunks must stay large enough to fill the GPU (>= 4096 one-warp jobs) — smaller ones lose more to partial waves
+// than the overlap wins
+static inline uint64_t pipeline_chunk(uint64_t B) {
+    if (B < 8192) return B;
+    uint64_t c = (B + 3) / 4;
+    return c < 4096 ? 4096 : c;
+}
+
 static inline uint32_t ceil_div_u64(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 // ---- internal entry points implemented across the .cu files (all take device pointers) -------------
@@ -162,6 +206,7 @@ int32_t normalize_points(vkzg_ctx* ctx, const xyzz_t* d_in, uint64_t n, affine_t
 int32_t build_window_tables(vkzg_ctx* ctx, Key& k);
 int32_t build_msm_tables(vkzg_ctx* ctx, Key& k);
 int32_t build_domain_tables(vkzg_ctx* ctx, Key& k);
+int32_t domain_for(vkzg_ctx* ctx, uint32_t lg, const DomainTables*& dt);
 // jobs x T-term fixed-base MSMs.  scalars[jobs][T] (Montgomery Fr).  ipa_m == 0: term t uses base t.
 // ipa_m != 0: the L/R cross-term base selection of an IPA round (commit.cu).  Result: out_xyzz[jobs].
 int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,

@@ -310,6 +310,21 @@ class Engine:
                                           dptr(d_slot), dptr(d_child), dptr(d_lit), ctypes.c_uint64(n_terms), dptr(d_nodes),
                                           dptr(d_out)), "vkzg_tree_level_dev")
 
+    # ---------------------------------------------------------------- KZG setup (next row 8f-2)
+    def kzg_setup(self, powers):
+        """powers [m,64] = [tau^i]G -> Lagrange-form SRS [next_pow2(m), 64] (group inverse FFT)"""
+        p = u8(powers, 64).reshape(-1, 64)
+        n = 1 << _log2(len(p))
+        out = np.zeros((n, 64), dtype=np.uint8)
+        check(self._L.vkzg_kzg_setup(self._ctx, hptr(p), ctypes.c_uint32(len(p)), hptr(out)), "vkzg_kzg_setup")
+        return out
+
+    def kzg_powers(self, gen_key, tau, m):
+        out = np.zeros((m, 64), dtype=np.uint8)
+        check(self._L.vkzg_kzg_powers(self._ctx, ctypes.c_uint32(gen_key.id), hptr(u8(tau, 32).reshape(32)), ctypes.c_uint32(m), hptr(out)),
+              "vkzg_kzg_powers")
+        return out
+
     # ---------------------------------------------------------------- probes
     def probe_imad(self, kind, blocks, threads, iters):
         macs = ctypes.c_uint64(0)

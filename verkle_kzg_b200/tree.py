@@ -12,7 +12,11 @@ Reference behaviour kept as is (the root commitment depends on it):
     (2 idx + 1) % W of C1 if idx < W/2 else C2, with W = key length in the reference (quirk Q6), 256 in the
     Ethereum layout; C = commit([1, from_le_bytes_mod_order(stem), to_data_item(C1), to_data_item(C2)]).
 """
+import ctypes
+
 import numpy as np
+
+from . import _lib
 
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 _MONT_R = 1 << 256
@@ -45,6 +49,8 @@ def _insert(root, key, value):
     n = len(key)
     node, depth = root, 0
     while True:
+        if depth >= n:
+            raise ValueError("internal chain deeper than the key")  # reference: index out of bounds
         k = key[depth]
         child = node.children.get(k)
         if child is None:
@@ -61,6 +67,8 @@ def _insert(root, key, value):
             d = depth + 1
             while d < n and child.stem[d] == key[d]:  # next_diff_depth, lib.rs:50-59
                 d += 1
+            if d >= n:  # the stems only differ above this depth: the reference indexes out of bounds (panic)
+                raise ValueError("stems differ only above the current depth")
             inner = _Int()
             e = _Ext(key)
             e.leaves[key[n - 1]] = value
@@ -186,3 +194,58 @@ class VerkleTree:
         if self._commit is None:
             self._commit = engine.tree_commit_levels(key, self.levels())
         return self._commit
+
+
+class NativeVerkleTree:
+    """The same interface over libvkzg's native host tree (vkzg_tree_*): C++ insertion, cached node commitments,
+    incremental recommit of the dirty paths.  Use this one for bulk work; `VerkleTree` above is the readable mirror."""
+
+    def __init__(self, key_len, ext_width=None):
+        self._L = _lib.lib()
+        self._L.vkzg_tree_nodes.restype = ctypes.c_uint64
+        self.key_len = key_len
+        self.ext_width = key_len if ext_width is None else ext_width
+        self._t = ctypes.c_void_p()
+        _lib.check(self._L.vkzg_tree_create(ctypes.byref(self._t), ctypes.c_uint32(key_len), ctypes.c_uint32(self.ext_width)),
+                   "vkzg_tree_create")
+        self.last_committed = 0
+
+    def close(self):
+        if self._t:
+            self._L.vkzg_tree_destroy(self._t)
+            self._t = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def insert_single(self, key, value):
+        self.insert_many(np.frombuffer(bytes(key), dtype=np.uint8).reshape(1, -1), np.frombuffer(bytes(value), dtype=np.uint8).reshape(1, 32))
+
+    def insert_many(self, keys, values):
+        keys = np.ascontiguousarray(keys, dtype=np.uint8)
+        values = np.ascontiguousarray(values, dtype=np.uint8)
+        assert keys.ndim == 2 and keys.shape[1] == self.key_len and values.shape == (len(keys), 32)
+        done = ctypes.c_uint64(0)
+        st = self._L.vkzg_tree_insert(self._t, _lib.hptr(keys), _lib.hptr(values), ctypes.c_uint64(len(keys)), ctypes.byref(done))
+        if st == -3:
+            raise ValueError(f"Traversed to extension node with differing stem (pair {done.value})")
+        _lib.check(st, "vkzg_tree_insert")
+
+    def get_single(self, key):
+        out = np.zeros(32, dtype=np.uint8)
+        k = np.frombuffer(bytes(key), dtype=np.uint8).copy()
+        return bytes(out) if self._L.vkzg_tree_get(self._t, _lib.hptr(k), _lib.hptr(out)) == 1 else None
+
+    @property
+    def nodes(self):
+        return int(self._L.vkzg_tree_nodes(self._t))
+
+    def commitment(self, engine, key):
+        out = np.zeros(64, dtype=np.uint8)
+        n = ctypes.c_uint64(0)
+        _lib.check(self._L.vkzg_tree_commit(engine._ctx, ctypes.c_uint32(key.id), self._t, _lib.hptr(out), ctypes.byref(n)), "vkzg_tree_commit")
+        self.last_committed = n.value
+        return out
