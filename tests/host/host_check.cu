@@ -46,11 +46,32 @@ int hc_g1_op(int mode, const uint8_t* a, const uint8_t* b, uint8_t* out) {
         r = xyzz_add(a2, b2);
     } else if (mode == 2) {
         r = xyzz_dbl(xyzz_from_affine(A));
-    } else {
+    } else if (mode == 3) {
         r = xyzz_from_affine(A);
         xyzz_madd(r, B);
         xyzz_madd(r, affine_neg(B));
         xyzz_madd(r, B);
+    } else if (mode == 4) {
+        // the kernels' hot path: lazily reduced accumulator ([0, 2p) coordinates), canonicalised once at the end.
+        // A + B - B + B + A - A  exercises addition, and the doubling / cancellation checks on lazy values
+        r = xyzz_from_affine(A);
+        xyzz_madd_hot(r, B);
+        xyzz_madd_hot(r, affine_neg(B));
+        xyzz_madd_hot(r, B);
+        xyzz_madd_hot(r, A);
+        xyzz_madd_hot(r, affine_neg(A));
+        xyzz_canon(r);
+    } else {
+        // mode 5: 2A via the doubling branch of the hot path, then + B, then (2A + B) - (2A + B) = infinity + B
+        r = xyzz_from_affine(A);
+        xyzz_madd_hot(r, A);
+        xyzz_madd_hot(r, B);
+        xyzz_t t = r;
+        xyzz_canon(t);
+        affine_t s = xyzz_to_affine(t);
+        xyzz_madd_hot(r, affine_neg(s));
+        xyzz_madd_hot(r, B);
+        xyzz_canon(r);
     }
     sta(out, xyzz_to_affine(r));
     return 0;

@@ -83,6 +83,11 @@ def test_group_ops(hc):
         assert orc.buf_to_pts(out)[0] is None
         hc.hc_g1_op(3, _p(buf[i]), _p(buf[(i + 1) % len(pts)]), _p(out))
         assert orc.buf_to_pts(out)[0] == pyref.g_add(pts[i], pts[(i + 1) % len(pts)])
+        # the kernels' lazily reduced mixed addition (xyzz_madd_hot + xyzz_canon)
+        hc.hc_g1_op(4, _p(buf[i]), _p(buf[(i + 1) % len(pts)]), _p(out))
+        assert orc.buf_to_pts(out)[0] == pyref.g_add(pts[i], pts[(i + 1) % len(pts)])
+        hc.hc_g1_op(5, _p(buf[i]), _p(buf[(i + 1) % len(pts)]), _p(out))
+        assert orc.buf_to_pts(out)[0] == pts[(i + 1) % len(pts)]
 
 
 @pytest.mark.parametrize("c", [4, 8, 13, 16, 20])

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
         }
         __syncwarp();
     }
+    xyzz_canon(acc);
 #pragma unroll 1
     for (int off = LPJ / 2; off > 0; off >>= 1) {
         xyzz_t o = shfl_xor_xyzz_c(acc, off);

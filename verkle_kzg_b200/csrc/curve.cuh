@@ -111,10 +111,12 @@ VK_HD void xyzz_madd(xyzz_t& acc, const affine_t& p) {
 // body of the accumulation kernels then is ~0.5 K instructions + one 3.5 KB multiplier instead of ~40 KB of
 // inlined code, i.e. it stays inside the instruction caches (ncu showed "no instruction" stalls otherwise).
 #ifdef __CUDA_ARCH__
-#define VK_MUL_HOT(a, b) fp_mul_ni<Q>(a, b)
+#define VK_MUL_HOT(a, b) fp_mul_lazy_ni<Q>(a, b)
 #else
-#define VK_MUL_HOT(a, b) fp_mul<Q>(a, b)
+#define VK_MUL_HOT(a, b) fp_mul_lazy<Q>(a, b)
 #endif
+// The accumulator coordinates are kept in [0, 2p) ("almost Montgomery": no final conditional subtraction in the ten
+// products); xyzz_canon() brings them back to [0, p) once, after the loop.  The table point is canonical.
 __host__ __device__ __forceinline__ void xyzz_madd_hot(xyzz_t& acc, const affine_t& p) {
     if (affine_is_inf(p)) return;
     if (xyzz_is_inf(acc)) {
@@ -123,10 +125,10 @@ __host__ __device__ __forceinline__ void xyzz_madd_hot(xyzz_t& acc, const affine
     }
     fp_t U2 = VK_MUL_HOT(p.x, acc.zz);
     fp_t S2 = VK_MUL_HOT(p.y, acc.zzz);
-    fp_t P = fp_sub<Q>(U2, acc.x);
-    fp_t R = fp_sub<Q>(S2, acc.y);
-    if (fp_is_zero(P)) {
-        if (fp_is_zero(R))
+    fp_t P = fp_sub_lazy<Q>(U2, acc.x);
+    fp_t R = fp_sub_lazy<Q>(S2, acc.y);
+    if (fp_is_zero_lazy<Q>(P)) {
+        if (fp_is_zero_lazy<Q>(R))
             acc = xyzz_dbl_affine(p);
         else
             acc = xyzz_inf();
@@ -135,12 +137,18 @@ __host__ __device__ __forceinline__ void xyzz_madd_hot(xyzz_t& acc, const affine
     fp_t PP = VK_MUL_HOT(P, P);
     fp_t PPP = VK_MUL_HOT(P, PP);
     fp_t Qv = VK_MUL_HOT(acc.x, PP);
-    fp_t X3 = fp_sub<Q>(fp_sub<Q>(VK_MUL_HOT(R, R), PPP), fp_dbl<Q>(Qv));
-    fp_t Y3 = fp_sub<Q>(VK_MUL_HOT(R, fp_sub<Q>(Qv, X3)), VK_MUL_HOT(acc.y, PPP));
+    fp_t X3 = fp_sub_lazy<Q>(fp_sub_lazy<Q>(VK_MUL_HOT(R, R), PPP), fp_add_lazy<Q>(Qv, Qv));
+    fp_t Y3 = fp_sub_lazy<Q>(VK_MUL_HOT(R, fp_sub_lazy<Q>(Qv, X3)), VK_MUL_HOT(acc.y, PPP));
     acc.x = X3;
     acc.y = Y3;
     acc.zz = VK_MUL_HOT(acc.zz, PP);
     acc.zzz = VK_MUL_HOT(acc.zzz, PPP);
+}
+__host__ __device__ __forceinline__ void xyzz_canon(xyzz_t& a) {
+    a.x = fp_canon<Q>(a.x);
+    a.y = fp_canon<Q>(a.y);
+    a.zz = fp_canon<Q>(a.zz);
+    a.zzz = fp_canon<Q>(a.zzz);
 }
 
 __host__ __device__ __noinline__ inline xyzz_t xyzz_dbl_ni(const xyzz_t p) { return xyzz_dbl(p); }

@@ -282,6 +282,96 @@ VK_HD fp_t fp_mul(const fp_t& a, const fp_t& b) {
     return r;
 }
 
+// "Almost Montgomery" product for the hot loops: inputs in [0, 2p), output in [0, 2p), NO final conditional
+// subtraction (R = 2^256 > 4p: (ab + mp)/R < 4p^2/R + p < 2p; the running total stays below 3p < 2^256).
+template <class P>
+VK_HD fp_t fp_mul_lazy(const fp_t& a, const fp_t& b) {
+    uint32_t u[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        uint64_t t0 = (uint64_t)a.l[j] * b.l[0];
+        uint64_t t1 = (uint64_t)a.l[j + 1] * b.l[0];
+        u[j] = (uint32_t)t0;
+        u[j + 1] = (uint32_t)(t0 >> 32);
+        v[j] = (uint32_t)t1;
+        v[j + 1] = (uint32_t)(t1 >> 32);
+    }
+    reduce_step<P>(u, v);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        {
+            uint32_t y[8];
+            shift_mad_row4(v[0], y, u, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+            mad_row4(v, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+            reduce_step<P>(v, y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = y[k];
+        }
+        if (i + 1 < 8) {
+            uint32_t y[8];
+            shift_mad_row4(u[0], y, v, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i + 1]);
+            mad_row4(u, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i + 1]);
+            reduce_step<P>(u, y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = y[k];
+        }
+    }
+    uint32_t vs[8];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) vs[k] = v[k + 1];
+    vs[7] = 0;
+    fp_t r;
+    add8(r.l, u, vs);
+    return r;
+}
+template <class P>
+__host__ __device__ __noinline__ fp_t fp_mul_lazy_ni(const fp_t a, const fp_t b) {
+    return fp_mul_lazy<P>(a, b);
+}
+// lazy add / sub / double on [0, 2p)
+template <class P>
+VK_HD fp_t fp_sub_lazy(const fp_t& a, const fp_t& b) {
+    fp_t r;
+    uint32_t borrow = sub8(r.l, a.l, b.l);
+    uint32_t pm[8], t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pm[k] = borrow & ((P::p(k) << 1) | (k ? P::p(k - 1) >> 31 : 0));  // 2p
+    add8(t, r.l, pm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = t[k];
+    return r;
+}
+template <class P>
+VK_HD fp_t fp_add_lazy(const fp_t& a, const fp_t& b) {
+    fp_t r;
+    add8(r.l, a.l, b.l);  // < 4p < 2^256: no carry out
+    uint32_t d[8], p2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p2[k] = (P::p(k) << 1) | (k ? P::p(k - 1) >> 31 : 0);
+    uint32_t borrow = sub8(d, r.l, p2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = borrow ? r.l[k] : d[k];
+    return r;
+}
+// [0, 2p) -> [0, p)
+template <class P>
+VK_HD fp_t fp_canon(const fp_t& a) {
+    fp_t r = a;
+    fp_cond_sub_p<P>(r.l, 0);
+    return r;
+}
+// a == 0 (mod p) for a in [0, 2p)
+template <class P>
+VK_HD bool fp_is_zero_lazy(const fp_t& a) {
+    uint32_t z = 0, e = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        z |= a.l[k];
+        e |= a.l[k] ^ P::p(k);
+    }
+    return z == 0 || e == 0;
+}
+
 template <class P>
 VK_HD fp_t fp_sqr(const fp_t& a) {
     return fp_mul<P>(a, a);

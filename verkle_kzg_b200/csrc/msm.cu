@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restric
         e = en;
         i = in;
     }
+    xyzz_canon(acc);
 #pragma unroll 1
     for (uint32_t m = 1; m < P; m <<= 1) {
         xyzz_t o = shfl_xor_xyzz(acc, (int)m);
