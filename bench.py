@@ -561,7 +561,12 @@ def run_native(args):
             "peak_source": "measured live: dependency-free mad.wide.u32 chains on all SMs (vkzg_probe_imad_dev); MEASURED_PEAKS.json has no integer figure",
             "work_model": f"{madds_per_unit} mixed additions per unit x {FQ_MUL_PER_MADD} Fq-mul x {MAC32_PER_FQ_MUL} MAC32",
             "kernel_launches_timed": kn, "kernel_ms_total": kms, "kernel_share_of_step": kms / ms if ms else None,
-            "traffic": None,
+            # DRAM bytes per launch: 128 B per table addition as ncu measured it on this kernel (dram__bytes_read.sum +
+            # dram__bytes_write.sum of one --set full capture, profiles/r01_ncu_full_summary_final.json: 1.785 GB for a
+            # launch of 13.7 M additions; every 64-byte point is fetched at 128-byte granularity) x additions per launch
+            "traffic": (units_per_step * madds_per_unit * args.steps / kn) * 128.0 if kn else None,
+            "algorithmic_bytes_per_launch": (units_per_step * madds_per_unit * args.steps / kn) * 64.0 if kn else None,
+            "ncu": "sm__pipe_fmaheavy_cycles_active 85 % (k_fixed_base_msm), 86 % (k_msm_bucket); DRAM read ~10 % of peak (profiles/)",
         },
     }
     if cpu_fn and not args.no_cpu_baseline:
