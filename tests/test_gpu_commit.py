@@ -142,3 +142,53 @@ def test_msm_degenerate_scalars(eng):
     minus1 = np.tile(orc.fr_to_buf([orc.R_MOD - 1])[0], (n, 1))
     assert (eng.msm(key, minus1) == orc.msm(bases, minus1, mode="pippenger")).all()
     key.free()
+
+
+def test_empty_and_degenerate_shapes(eng, key257):
+    """B = 0 and n = 0 are no-ops; a key that is not a power of two still commits (IPA / quotients refuse it)"""
+    from verkle_kzg_b200 import VkzgError
+    bases, key = key257
+    assert eng.commit_batch(key, np.zeros((0, 256, 32), dtype=np.uint8)).shape == (0, 64)
+    assert eng.to_data_item(np.zeros((0, 64), dtype=np.uint8)).shape == (0, 32)
+    assert not eng.g1_sum(np.zeros((0, 64), dtype=np.uint8)).any()
+    rng = np.random.default_rng(3)
+    k5 = eng.load_key(bases[:5], q=bases[5], window_bits=8)          # width 5: not a power of two
+    s = orc.rand_fr_buf(rng, 2 * 5).reshape(2, 5, 32)
+    assert (eng.commit_batch(k5, s) == orc.commit_batch(bases[:5], s)).all()
+    with pytest.raises(VkzgError) as ei:                              # the reference's split() breaks on odd lengths
+        eng.ipa_prove_batch(k5, s, orc.fr_to_buf([1, 2]), eng.commit_batch(k5, s))
+    assert ei.value.status == -4
+    k5.free()
+    mk = eng.load_key(bases[:8], kind=2, window_bits=8)
+    assert not eng.msm(mk, np.zeros((0, 32), dtype=np.uint8)).any()  # empty MSM = identity
+    with pytest.raises(VkzgError):
+        eng.msm(mk, np.zeros((9, 32), dtype=np.uint8))                # more scalars than bases in the key
+    mk.free()
+
+
+def test_commit_with_identity_bases(eng):
+    """a key may contain the point at infinity (e.g. a zero Lagrange commitment): its terms vanish"""
+    rng = np.random.default_rng(4)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, 8)
+    bases[2] = 0
+    bases[7] = 0
+    key = eng.load_key(bases, window_bits=8)
+    s = orc.rand_fr_buf(rng, 3 * 8).reshape(3, 8, 32)
+    assert (eng.commit_batch(key, s) == orc.commit_batch(bases, s)).all()
+    key.free()
+    mk = eng.load_key(bases, kind=2, window_bits=8)
+    assert (eng.msm(mk, s[0]) == orc.msm(bases, s[0])).all()
+    mk.free()
+
+
+def test_large_window_bits_and_sparse_scalars(eng):
+    """c = 18 tables (more entries per row than c = 16) and sparse / small scalars (many zero digits)"""
+    rng = np.random.default_rng(6)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, 3)
+    key = eng.load_key(bases, window_bits=18)
+    vals = [[1, 0, 2 ** 128 - 1], [0, 0, 0], [2 ** 17, 2 ** 18 - 1, 2 ** 35], [orc.R_MOD - 1, 2 ** 253, 12345]]
+    s = np.stack([orc.fr_to_buf(v) for v in vals])
+    assert (eng.commit_batch(key, s) == orc.commit_batch(bases, s)).all()
+    key.free()

@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(128) k_sum_slices(const xyzz_t* __restrict__ p
 template <int LPJ>
 static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                                  uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, uint32_t split, xyzz_t* d_out) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device: one process may hold contexts on several GPUs
+    if (ctx->device >= 64 || !attr_set[ctx->device]) {
         VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm<LPJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VK_CUDA(cudaFuncSetAttribute(k_fixed_base_msm<LPJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+        if (ctx->device < 64) attr_set[ctx->device] = true;
     }
     size_t smem = (size_t)WARPS_PER_CTA * (CHUNK_TERMS * k.W + 32) * sizeof(uint32_t);
     uint64_t per_cta = (uint64_t)WARPS_PER_CTA * (32 / LPJ);

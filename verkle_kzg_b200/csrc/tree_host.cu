@@ -9,7 +9,6 @@
 // k_fixed_base_msm in CSR mode), feeding clean children in as already-known commitments.
 #include <algorithm>
 #include <array>
-#include <string>
 
 #include "vk_common.cuh"
 
@@ -25,11 +24,10 @@ struct HNode {
     // internal
     std::vector<std::pair<uint8_t, uint32_t>> kids;  // (unit, node id), unsorted; direct table once it grows
     std::vector<int32_t> table;                      // 256 entries or empty
-    // extension
-    std::string stem;
-    std::vector<std::pair<uint8_t, std::array<uint8_t, 32>>> leaves;
-    // scratch of one commit pass
-    int32_t level = -1, gid = -1;
+    // extension: the stem lives in the tree's byte arena (no per-node heap allocation), the first leaf inline
+    uint64_t stem_off = 0;
+    uint8_t leaf_unit = 0;
+    std::array<uint8_t, 32> leaf_val;
 };
 
 }  // namespace vk
@@ -37,7 +35,9 @@ struct HNode {
 struct vkzg_tree {
     uint32_t key_len = 0, ext_width = 0;
     std::vector<vk::HNode> nodes;  // node 0 is the root
+    std::vector<uint8_t> stems;    // key bytes of every extension node
     uint64_t n_keys = 0;
+    const uint8_t* stem(const vk::HNode& n) const { return stems.data() + n.stem_off; }
 
     int32_t child(uint32_t id, uint8_t unit) const {
         const vk::HNode& n = nodes[id];
@@ -63,13 +63,13 @@ struct vkzg_tree {
         }
     }
     uint32_t new_ext(const uint8_t* key, const uint8_t* value) {
-        vk::HNode e;
+        nodes.emplace_back();
+        vk::HNode& e = nodes.back();
         e.internal = false;
-        e.stem.assign((const char*)key, key_len);
-        std::array<uint8_t, 32> v;
-        memcpy(v.data(), value, 32);
-        e.leaves.push_back({key[key_len - 1], v});
-        nodes.push_back(std::move(e));
+        e.stem_off = stems.size();
+        stems.insert(stems.end(), key, key + key_len);
+        e.leaf_unit = key[key_len - 1];
+        memcpy(e.leaf_val.data(), value, 32);
         return (uint32_t)nodes.size() - 1;
     }
     // Node::insert (node.rs:133-197).  Returns false where the reference panics (differing stem, node.rs:139-141).
@@ -88,31 +88,20 @@ struct vkzg_tree {
             }
             if (!nodes[c].internal) {
                 vk::HNode& ext = nodes[c];
-                bool same = memcmp(ext.stem.data(), key, key_len) == 0;
+                const uint8_t* est = stem(ext);
+                bool same = memcmp(est, key, key_len) == 0;
                 if (same || depth == key_len - 2) {
                     if (!same) return false;
                     ext.clean = false;
-                    std::array<uint8_t, 32> v;
-                    memcpy(v.data(), value, 32);
-                    bool found = false;
-                    for (auto& lf : ext.leaves)
-                        if (lf.first == key[key_len - 1]) {
-                            lf.second = v;
-                            found = true;
-                        }
-                    if (!found) {
-                        ext.leaves.push_back({key[key_len - 1], v});
-                        ++n_keys;
-                    }
+                    // same stem means same key, hence the same leaf unit: overwrite (node.rs:142-146)
+                    memcpy(ext.leaf_val.data(), value, 32);
                     return true;
                 }
                 uint32_t d = depth + 1;  // next_diff_depth (lib.rs:50-59)
-                while (d < key_len && (uint8_t)ext.stem[d] == key[d]) ++d;
+                while (d < key_len && est[d] == key[d]) ++d;
                 if (d >= key_len) return false;  // the stems only differ above this depth: the reference indexes out of bounds
-                uint8_t old_unit = (uint8_t)ext.stem[d];
-                vk::HNode in;
-                in.internal = true;
-                nodes.push_back(std::move(in));
+                uint8_t old_unit = est[d];
+                nodes.emplace_back();
                 uint32_t inner = (uint32_t)nodes.size() - 1;
                 uint32_t e = new_ext(key, value);
                 set_child(inner, key[d], e);
@@ -135,10 +124,8 @@ struct vkzg_tree {
             ++depth;
         }
         const vk::HNode& e = nodes[cur];
-        if (memcmp(e.stem.data(), key, key_len) != 0) return nullptr;
-        for (auto& lf : e.leaves)
-            if (lf.first == key[key_len - 1]) return lf.second.data();
-        return nullptr;
+        if (memcmp(stem(e), key, key_len) != 0) return nullptr;
+        return e.leaf_unit == key[key_len - 1] ? e.leaf_val.data() : nullptr;
     }
 };
 
@@ -195,6 +182,8 @@ int32_t vkzg_tree_destroy(vkzg_tree* t) {
 // *n_done = pairs inserted)
 int32_t vkzg_tree_insert(vkzg_tree* t, const uint8_t* keys, const uint8_t* values, uint64_t n, uint64_t* n_done) {
     if (!t || (n && (!keys || !values))) return VKZG_ERR_ARG;
+    t->nodes.reserve(t->nodes.size() + n + n / 4 + 16);
+    t->stems.reserve(t->stems.size() + n * t->key_len);
     for (uint64_t i = 0; i < n; ++i) {
         if (!t->insert(keys + i * t->key_len, values + i * 32)) {
             if (n_done) *n_done = i;
@@ -256,11 +245,11 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
                     }
                 v.push_back({s, x});
             };
-            for (auto& lf : n.leaves) {
-                uint32_t idx = lf.first;
+            {
+                uint32_t idx = n.leaf_unit;
                 auto& tgt = idx < W / 2 ? c1 : c2;
-                put(tgt, (uint16_t)((2 * idx) % W), fr_from_le_bytes(lf.second.data(), 16));
-                put(tgt, (uint16_t)((2 * idx + 1) % W), fr_from_le_bytes(lf.second.data() + 16, 16));
+                put(tgt, (uint16_t)((2 * idx) % W), fr_from_le_bytes(n.leaf_val.data(), 16));
+                put(tgt, (uint16_t)((2 * idx + 1) % W), fr_from_le_bytes(n.leaf_val.data() + 16, 16));
             }
             int32_t r1 = -1, r2 = -1;
             if (!c1.empty()) {
@@ -273,7 +262,7 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
             }
             // node.rs:243-253: commit([1, stem, C1, C2]); child ids are patched to global ids below (level 0 rows)
             levels[1].term(0, -1, one);
-            levels[1].term(1, -1, fr_from_le_bytes((const uint8_t*)n.stem.data(), n.stem.size()));
+            levels[1].term(1, -1, fr_from_le_bytes(t->stem(n), t->key_len));
             if (r1 >= 0) levels[1].term(2, -(r1 + 2), zero);  // encoded: -(row + 2) = level-0 row, resolved after layout
             if (r2 >= 0) levels[1].term(3, -(r2 + 2), zero);
             handle[id] = {1u, (int32_t)levels[1].close(id)};
