@@ -208,6 +208,18 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
     if (jobs == 0) return VKZG_OK;
     if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 8) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
+    // big dense batches: fewer lanes per job shorten the shuffle-tree fold (log2(lanes) full additions per job) as long as
+    // enough warps remain to fill the GPU several times over
+    if (!d_row_ptr && lanes_per_job == 0) {
+        static int dense_lpj = -1;
+        if (dense_lpj < 0) {
+            const char* e = getenv("VKZG_FB_LPJ");  // tuning knob (8, 16 or 32)
+            dense_lpj = e ? atoi(e) : 8;
+        }
+        uint64_t warps16 = jobs / 2, warps8 = jobs / 4, fill = (uint64_t)ctx->sm_count * 16;
+        if (dense_lpj == 8 && warps8 >= 3 * fill) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, 1, d_out);
+        if (dense_lpj <= 16 && warps16 >= 3 * fill) return launch_fixed_base<16>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, 1, d_out);
+    }
     // few wide dense jobs (single proofs / commits): slice every job over several warps so the whole GPU works on it
     if (!d_row_ptr && T >= 16 && jobs * 8 <= (uint64_t)ctx->sm_count * 16) {
         uint32_t split = (T + 7) / 8;  // ~8 terms (128 table additions) per warp
