@@ -349,12 +349,12 @@ def run_native(args):
                 eng.ipa_prove_batch_dev(key, a, z, C, B, Lr, Rr, tip, y)
 
             def step_e2e():
-                check(L.vkzg_commit_batch(eng._ctx, kid, hp(a_h), ctypes.c_uint32(N_WIDTH), ctypes.c_uint64(B), hp(C_h)), "commit")
-                check(L.vkzg_ipa_prove_batch(eng._ctx, kid, hp(a_h), hp(z_h), hp(C_h), ctypes.c_uint64(B), None, ctypes.c_uint32(0), b"ipa",
-                                             hp(L_h), hp(R_h), hp(tip_h), hp(y_h)), "prove")
+                # host buffers in, host buffers out: commit + open through the batch entry point (one upload of the rows)
+                check(L.vkzg_ipa_commit_prove_batch(eng._ctx, kid, hp(a_h), hp(z_h), ctypes.c_uint64(B), hp(C_h), hp(L_h), hp(R_h),
+                                                    hp(tip_h), hp(y_h)), "commit_prove")
             madds_per_unit = (N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * WINDOWS          # commit + 8 rounds of two 129-term MSMs
             launches_timed = 9
-            h2d = 2 * a_h.numel() + z_h.numel() + C_h.numel()
+            h2d = a_h.numel() + z_h.numel()
             d2h = C_h.numel() + L_h.numel() + R_h.numel() + tip_h.numel() + y_h.numel()
             metric, unit = "ipa_commit_and_prove_proofs_per_s", "proofs/s"
             cfg = {"workload": "configs[1]: Pedersen/IPA commit + low_level_ipa proof, width 256, batch 2^14 vectors per GPU",
@@ -521,15 +521,20 @@ def run_native(args):
         cfg["window_bits"] = WINDOW_BITS
         cfg["window_table_gb"] = round(key.table_bytes / 1e9, 1)
     cfg["l2_policy"] = "tables (GBs) and inputs (>= 128 MB) exceed the 126 MB L2; no flush needed"
-    # ---- device-resident timing, with the dominant kernel bracketed by its own event pairs
-    for _ in range(args.warmup):
-        step()
-    eng.kernel_timing(True)
+    # ---- device-resident timing (the `value`): W warm-up steps, K timed steps
     l0 = eng.launches
-    ms, clocks = timed_steps(torch, dist, world, step, args.steps, 0, sampler)
-    launches = eng.launches - l0
+    ms, clocks = timed_steps(torch, dist, world, step, args.steps, args.warmup, sampler)
+    launches = (eng.launches - l0) * args.steps // (args.steps + args.warmup)
+    # ---- the dominant kernel's own launch durations (roofline): every launch bracketed by a CUDA event pair on its stream.
+    #      Taken in a second pass of K steps with the IPA half-batches on ONE stream, so that a bracket times one kernel alone
+    #      (in the timed region above the two half-batches interleave on two streams and brackets would overlap).
+    eng.set_option(1, 0)
+    step()
+    eng.kernel_timing(True)
+    ms_k, _ = timed_steps(torch, dist, world, step, args.steps, 0)
     kn, kms = eng.kernel_timing_read()
     eng.kernel_timing(False)
+    eng.set_option(1, 1)
     if world > 1:
         tu = torch.tensor([units_per_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(tu)
@@ -560,7 +565,8 @@ def run_native(args):
             "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": "measured live: dependency-free mad.wide.u32 chains on all SMs (vkzg_probe_imad_dev); MEASURED_PEAKS.json has no integer figure",
             "work_model": f"{madds_per_unit} mixed additions per unit x {FQ_MUL_PER_MADD} Fq-mul x {MAC32_PER_FQ_MUL} MAC32",
-            "kernel_launches_timed": kn, "kernel_ms_total": kms, "kernel_share_of_step": kms / ms if ms else None,
+            "kernel_launches_timed": kn, "kernel_ms_total": kms, "kernel_share_of_step": kms / ms_k if ms_k else None,
+            "one_stream_ms_per_step": ms_k / args.steps,
             # DRAM bytes per launch: 128 B per table addition as ncu measured it on this kernel (dram__bytes_read.sum +
             # dram__bytes_write.sum of one --set full capture, profiles/r01_ncu_full_summary_final.json: 1.785 GB for a
             # launch of 13.7 M additions; every 64-byte point is fetched at 128-byte granularity) x additions per launch

@@ -56,6 +56,10 @@ int32_t vkzg_ctx_create(vkzg_ctx** out, int32_t device_id);
 int32_t vkzg_ctx_create_on_stream(vkzg_ctx** out, int32_t device_id, void* cuda_stream);
 int32_t vkzg_ctx_destroy(vkzg_ctx* ctx);
 int32_t vkzg_ctx_sync(vkzg_ctx* ctx);
+/* options: VKZG_OPT_IPA_TWO_STREAMS (default 1): batches of >= 8192 IPA proofs run as two half-batches on two streams so
+ * that one half's latency-bound challenge / fold kernels hide under the other half's MSM kernel                      */
+enum { VKZG_OPT_IPA_TWO_STREAMS = 1 };
+int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 uint64_t vkzg_ctx_launches(const vkzg_ctx* ctx);
 
@@ -130,6 +134,10 @@ int32_t vkzg_ipa_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, c
 int32_t vkzg_ipa_prove_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_a, const vkzg_fr* d_points,
                                  const vkzg_g1_affine* d_commitments, uint64_t B, const uint8_t* prefix, uint32_t prefix_len,
                                  const char* dst, vkzg_g1_affine* d_L, vkzg_g1_affine* d_R, vkzg_fr* d_tip, vkzg_fr* d_y);
+/* IPA::commit followed by IPA::prove_point on the same B vectors in ONE call (fresh "ipa" transcripts): the rows cross
+ * PCIe once and the commitments stay on the device between the two steps.  Outputs: commitments[B] + the proofs.    */
+int32_t vkzg_ipa_commit_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, const vkzg_fr* points, uint64_t B,
+                                    vkzg_g1_affine* commitments, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* y);
 /* ---- I3: IPA::verify_point + low_level_verify_ipa (ipa/mod.rs:165-181, :321-360), batched ------------ */
 /* ok[B] receives 1 (valid) / 0 (invalid) */
 int32_t vkzg_ipa_verify_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* points, const vkzg_g1_affine* commitments,

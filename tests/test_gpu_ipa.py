@@ -141,3 +141,17 @@ def test_batch_roundtrip_full_width(eng):
         eL, eR, etip, ey = orc.ipa_prove(bases, N, a[i], C[i], zb[i])
         assert (L[i] == eL).all() and (R[i] == eR).all() and (tip[i] == etip).all() and (y[i] == ey).all()
     key.free()
+
+
+def test_commit_prove_in_one_call(eng):
+    N = 32
+    rng, bases, key = _setup(eng, N, 82, 12)
+    B = 6
+    a = orc.rand_fr_buf(rng, B * N).reshape(B, N, 32)
+    zb = orc.fr_to_buf(_points(rng, N, B))
+    C, L, R, tip, y = eng.ipa_commit_prove_batch(key, a, zb)
+    C2 = eng.commit_batch(key, a)
+    L2, R2, tip2, y2 = eng.ipa_prove_batch(key, a, zb, C2)
+    assert (C == C2).all() and (L == L2).all() and (R == R2).all() and (tip == tip2).all() and (y == y2).all()
+    assert (C == orc.commit_batch(bases[:N], a)).all()
+    key.free()

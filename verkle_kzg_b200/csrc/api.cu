@@ -73,6 +73,7 @@ int32_t vkzg_ctx_destroy(vkzg_ctx* ctx) {
     }
     for (auto& kv : ctx->domains) cudaFree(kv.second.omega);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VKZG_OK;
@@ -85,6 +86,14 @@ int32_t vkzg_ctx_sync(vkzg_ctx* ctx) {
 }
 
 uint64_t vkzg_ctx_launches(const vkzg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value) {
+    VK_TRY(ctx_check(ctx));
+    switch (option) {
+        case VKZG_OPT_IPA_TWO_STREAMS: ctx->ipa_two_streams = value != 0; return VKZG_OK;
+        default: return VKZG_ERR_ARG;
+    }
+}
 
 int32_t vkzg_ctx_kernel_timing(vkzg_ctx* ctx, int32_t enable) {
     VK_TRY(ctx_check(ctx));

@@ -233,9 +233,42 @@ static int32_t make_prefix(TrPrefix& pre, const uint8_t* prefix, uint32_t prefix
     return VKZG_OK;
 }
 
+static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
+                                    const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst,
+                                    affine_t* d_L, affine_t* d_R, fp_t* d_tip, fp_t* d_y);
+
+// Big batches are proven as two half-batches on two streams: the per-round challenge / fold kernels are latency-bound
+// (a thread or a warp per proof, 8 dependent rounds), so one half's hash-and-fold runs under the other half's MSM kernel.
+int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
+                       const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,
+                       affine_t* d_R, fp_t* d_tip, fp_t* d_y) {
+    if (!ctx->ipa_two_streams || B < 8192)
+        return ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y);
+    if (!ctx->aux_stream) VK_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    uint32_t rounds = 0;
+    while ((1u << rounds) < N) ++rounds;
+    const uint64_t B0 = B / 2, B1 = B - B0;
+    cudaEvent_t fork, join;
+    VK_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    VK_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    VK_CUDA(cudaEventRecord(fork, ctx->stream));          // inputs are ready in main-stream order
+    VK_CUDA(cudaStreamWaitEvent(ctx->aux_stream, fork, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->aux_stream;                        // everything the second half enqueues (scratch included) goes to the aux stream
+    int32_t st1 = ipa_prove_one_stream(ctx, k, mode, N, d_a + B0 * N, d_points ? d_points + B0 : nullptr, d_C + B0, B1, prefix, prefix_len,
+                                       dst, d_L + B0 * rounds, d_R + B0 * rounds, d_tip + B0, d_y + B0);
+    cudaEventRecord(join, ctx->stream);
+    ctx->stream = main_stream;
+    int32_t st0 = ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B0, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y);
+    cudaStreamWaitEvent(ctx->stream, join, 0);
+    cudaEventDestroy(fork);
+    cudaEventDestroy(join);
+    return st0 != VKZG_OK ? st0 : st1;
+}
+
 // mode 0: prove_point (b from the evaluation point, q term); mode 1: prove_commitment (no b, no q).
 // N = vector length (power of two, <= key size).
-int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
+static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                        const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,
                        affine_t* d_R, fp_t* d_tip, fp_t* d_y) {
     if (B == 0) return VKZG_OK;
@@ -481,6 +514,46 @@ int32_t vkzg_ipa_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, c
         VK_TRY(ipa_prove_core(ctx, *k, 0, N, da.p + b0 * N, dp.p + b0, dc.p + b0, nb, prefix, prefix_len, dst, dL.p + b0 * rounds,
                               dR.p + b0 * rounds, dtip.p + b0, dy.p + b0));
     }
+    VK_TRY(download(ctx, L, dL.p, B * rounds));
+    VK_TRY(download(ctx, R, dR.p, B * rounds));
+    VK_TRY(download(ctx, tip, dtip.p, B));
+    VK_TRY(download(ctx, y, dy.p, B));
+    return stream_sync(ctx);
+}
+
+// commit + open in one call: the rows cross PCIe once (chunked, overlapped with the commit kernels), the commitments
+// never leave the device between the two steps
+int32_t vkzg_ipa_commit_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, const vkzg_fr* points, uint64_t B,
+                                    vkzg_g1_affine* commitments, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || !k->has_q) return VKZG_ERR_ARG;
+    if (B && (!a || !points || !commitments || !L || !R || !tip || !y)) return VKZG_ERR_ARG;
+    uint32_t N = k->n, rounds = k->log2n;
+    if (B == 0) return VKZG_OK;
+    DevBuf<fp_t> da, dp, dtip, dy;
+    DevBuf<affine_t> dc, dL, dR;
+    DevBuf<xyzz_t> acc;
+    VK_TRY(da.alloc(ctx, B * N));
+    VK_TRY(upload(ctx, dp, points, B));
+    VK_TRY(dc.alloc(ctx, B));
+    VK_TRY(acc.alloc(ctx, B));
+    VK_TRY(dL.alloc(ctx, B * rounds));
+    VK_TRY(dR.alloc(ctx, B * rounds));
+    VK_TRY(dtip.alloc(ctx, B));
+    VK_TRY(dy.alloc(ctx, B));
+    ChunkedUpload up(ctx);
+    VK_TRY(up.init());
+    const uint64_t chunk = pipeline_chunk(B);
+    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
+        uint64_t nb = B - b0 < chunk ? B - b0 : chunk;
+        VK_TRY(up.copy(da.p + b0 * N, (const fp_t*)a + b0 * N, nb * N * sizeof(fp_t)));
+        VK_TRY(up.publish());
+        VK_TRY(fixed_base_msm(ctx, *k, da.p + b0 * N, N, nb, 0, 0xffffffffu, acc.p + b0));
+    }
+    VK_TRY(normalize_points(ctx, acc, B, dc));
+    VK_TRY(ipa_prove_core(ctx, *k, 0, N, da, dp, dc, B, nullptr, 0, "ipa", dL, dR, dtip, dy));
+    VK_TRY(download(ctx, commitments, dc.p, B));
     VK_TRY(download(ctx, L, dL.p, B * rounds));
     VK_TRY(download(ctx, R, dR.p, B * rounds));
     VK_TRY(download(ctx, tip, dtip.p, B));

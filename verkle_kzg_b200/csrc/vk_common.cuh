@@ -70,6 +70,8 @@ struct vkzg_ctx {
     // optional per-kernel timing of the dominant kernel (bench.py's roofline): CUDA event pairs around
     // every k_fixed_base_msm / k_msm_bucket launch on this context's stream
     cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
+    cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
+    bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     uint64_t timing_units = 0;  // point additions issued by the timed launches (upper bound: zero digits excluded at run time)

@@ -63,6 +63,9 @@ class Engine:
     def launches(self):
         return int(self._L.vkzg_ctx_launches(self._ctx))
 
+    def set_option(self, option, value):
+        check(self._L.vkzg_ctx_set_option(self._ctx, ctypes.c_int32(option), ctypes.c_int32(value)), "vkzg_ctx_set_option")
+
     def kernel_timing(self, enable=True):
         check(self._L.vkzg_ctx_kernel_timing(self._ctx, ctypes.c_int32(1 if enable else 0)), "vkzg_ctx_kernel_timing")
 
@@ -178,6 +181,22 @@ class Engine:
                                            ctypes.c_uint64(B), hptr(pre), ctypes.c_uint32(plen), dst.encode(), hptr(L), hptr(R),
                                            hptr(tip), hptr(y)), "vkzg_ipa_prove_batch")
         return L, R, tip, y
+
+    def ipa_commit_prove_batch(self, key, a, points):
+        """commit + open in one call -> (C [B,64], L, R, tip, y)"""
+        a = u8(a, 32)
+        B, N = a.shape[0], a.shape[1]
+        assert N == key.n
+        points = u8(points, 32).reshape(B, 32)
+        lg = key.log2n
+        C = np.zeros((B, 64), dtype=np.uint8)
+        L = np.zeros((B, lg, 64), dtype=np.uint8)
+        R = np.zeros((B, lg, 64), dtype=np.uint8)
+        tip = np.zeros((B, 32), dtype=np.uint8)
+        y = np.zeros((B, 32), dtype=np.uint8)
+        check(self._L.vkzg_ipa_commit_prove_batch(self._ctx, ctypes.c_uint32(key.id), hptr(a), hptr(points), ctypes.c_uint64(B), hptr(C),
+                                                  hptr(L), hptr(R), hptr(tip), hptr(y)), "vkzg_ipa_commit_prove_batch")
+        return C, L, R, tip, y
 
     def ipa_prove_batch_dev(self, key, d_a, d_points, d_commitments, B, d_L, d_R, d_tip, d_y, prefix=b"", dst="ipa"):
         pre, plen = self._prefix(prefix)
