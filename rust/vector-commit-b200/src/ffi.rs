@@ -53,8 +53,16 @@ extern "C" {
     pub fn vkzg_tree_commit_levels(ctx: *mut vkzg_ctx, key_id: u32, n_levels: u32, nodes_per_level: *const u64,
                                    row_ptr: *const *const u32, slot: *const *const u16, child: *const *const i32,
                                    lit: *const *const vkzg_fr, root_out: *mut vkzg_g1_affine) -> i32;
+    pub fn vkzg_ipa_commit_prove_batch(ctx: *mut vkzg_ctx, key_id: u32, a: *const vkzg_fr, points: *const vkzg_fr, b: u64,
+                                       commitments: *mut vkzg_g1_affine, l: *mut vkzg_g1_affine, r: *mut vkzg_g1_affine,
+                                       tip: *mut vkzg_fr, y: *mut vkzg_fr) -> i32;
+    pub fn vkzg_kzg_setup(ctx: *mut vkzg_ctx, powers: *const vkzg_g1_affine, m: u32, lagrange: *mut vkzg_g1_affine) -> i32;
+    pub fn vkzg_tree_create(out: *mut *mut Opaque, key_len: u32, ext_width: u32) -> i32;
+    pub fn vkzg_tree_insert(tree: *mut Opaque, keys: *const u8, values: *const u8, n: u64, n_done: *mut u64) -> i32;
+    pub fn vkzg_tree_get(tree: *const Opaque, key: *const u8, value_out: *mut u8) -> i32;
+    pub fn vkzg_tree_commit(ctx: *mut vkzg_ctx, key_id: u32, tree: *mut Opaque, root_out: *mut vkzg_g1_affine, n_committed: *mut u64) -> i32;
+    pub fn vkzg_tree_destroy(tree: *mut Opaque) -> i32;
     pub fn vkzg_ctx_sync(ctx: *mut vkzg_ctx) -> i32;
 }
 
-#[allow(dead_code)]
 pub type Opaque = c_void;
