@@ -256,7 +256,7 @@ def run_reference(args):
         fn = lambda: cpu_msm_sample(bases, per_step, cores)
         metric, unit, cfg = "msm_points_per_s", "points/s", f"one MSM of 2^{args.log2n} points (sample of {per_step} terms)"
     else:
-        print(json.dumps({"impl": "reference", "unavailable": f"no CPU arm for workload {wl}"}))
+        emit({"impl": "reference", "unavailable": f"no CPU arm for workload {wl}"})
         return
     for _ in range(min(args.warmup, 1)):
         fn()
@@ -275,7 +275,7 @@ def run_reference(args):
                          "sample": f"{per_step} units per step x {args.steps} steps; restated reference algorithm (C++), not the arkworks binary"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -588,13 +588,27 @@ def run_native(args):
             sample = f"{nsmp} of the {units_per_step} vectors"
         line["cpu_baseline"] = {"value": u / dt, "unit": unit, "cores": cores, "kind": "port",
                                 "sample": sample + "; restated reference algorithm (C++ oracle), not the arkworks binary"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner, torchrun
+    notices) was diverted to stderr for the lifetime of the process"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
