@@ -575,7 +575,7 @@ def run_native(args):
             "ncu": "sm__pipe_fmaheavy_cycles_active 85 % (k_fixed_base_msm), 86 % (k_msm_bucket); DRAM read ~10 % of peak (profiles/)",
         },
     }
-    if cpu_fn and not args.no_cpu_baseline:
+    if cpu_fn and not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
         cores = cpu_cores()
         if wl == "msm":
             nsmp = 128 * cores

@@ -64,6 +64,23 @@ def test_field_ops(hc, tag, mod):
     assert [int.from_bytes(bytes(r), "little") for r in got] == want
 
 
+@pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
+def test_lazy_reduction_ops(hc, tag, mod):
+    """the hot loops' "almost Montgomery" arithmetic: raw representatives anywhere in [0, 2p), results correct mod p"""
+    rng = np.random.default_rng(300 + tag)
+    edge = [0, 1, mod - 1, mod, mod + 1, 2 * mod - 1, 2 * mod - 2, (1 << 254) - 1, (1 << 254), mod + (1 << 253)]
+    edge = [e for e in edge if e < 2 * mod]
+    xs = [int.from_bytes(rng.bytes(32), "little") % (2 * mod) for _ in range(300)] + edge + edge
+    ys = [int.from_bytes(rng.bytes(32), "little") % (2 * mod) for _ in range(300)] + edge + edge[::-1]
+    raw = lambda v: np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in v), dtype=np.uint8).reshape(-1, 32).copy()
+    a, b = raw(xs), raw(ys)
+    rinv = pow(orc.MONT_R, -1, mod)
+    val = lambda buf: [int.from_bytes(bytes(r), "little") for r in buf]
+    assert val(_op(hc, tag, 8, a, b)) == [(x * y * rinv) % mod for x, y in zip(xs, ys)]
+    assert val(_op(hc, tag, 9, a, b)) == [(x - y) % mod for x, y in zip(xs, ys)]
+    assert val(_op(hc, tag, 10, a, b)) == [(x + y) % mod for x, y in zip(xs, ys)]
+
+
 def test_group_ops(hc):
     rng = np.random.default_rng(7)
     ks = orc.rand_fr(rng, 6) + [1, 2]
