@@ -73,6 +73,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """start of the timed region: earlier samples are kept only if the region turns out shorter than one sampling period"""
+        self.first = max(0, len(self.rows) - 1)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -81,6 +85,8 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        self.rows = rows
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -142,13 +148,15 @@ def dist_setup(args):
 
 def timed_steps(torch, dist, world, fn, steps, warmup, sampler=None):
     """W warm-up steps, then K steps between barrier + synchronize; CUDA events on the launching stream; max over ranks"""
+    if sampler:
+        sampler.start()  # nvidia-smi needs ~0.2 s to deliver its first sample: start it under the (identical) warm-up load
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     if sampler:
-        sampler.start()
+        sampler.mark()   # only samples from here on count
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     a.record()

@@ -1,5 +1,5 @@
-"""Randomised parity sweep (not part of the test-suite): libvkzg against the oracle on random shapes and seeds.
-    python tools/fuzz_parity.py [seconds]"""
+"""Randomised parity sweep (test infrastructure, not collected by pytest): libvkzg against the oracle on random shapes
+and seeds.      python tests/fuzz_parity.py [seconds]"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import orc  # noqa: E402
 from verkle_kzg_b200 import Engine  # noqa: E402
 

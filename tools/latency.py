@@ -5,12 +5,19 @@ import sys
 import time
 
 import numpy as np
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import orc  # noqa: E402  (test-only helper: builds a CRS and random vectors on the CPU)
+import bench  # noqa: E402  (synthetic CRS / vectors made on the device by the product itself)
 from verkle_kzg_b200 import Engine  # noqa: E402
+
+R_MOD = bench.R_MOD
+
+
+def fr(vals):
+    """F::from(v) in the ABI layout (Montgomery)"""
+    return np.stack([np.frombuffer(((int(v) << 256) % R_MOD).to_bytes(32, "little"), dtype=np.uint8) for v in vals])
 
 
 def timeit(fn, reps=20):
@@ -24,12 +31,13 @@ def timeit(fn, reps=20):
 def main():
     eng = Engine(0)
     rng = np.random.default_rng(1)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1)
     N = 256
-    k0, k1 = orc.rand_fr(rng, 2)
-    bases = orc.points_walk(k0, k1, N + 1)
+    bases = bench.make_points_dev(torch, eng, N + 1, gen).cpu().numpy()
     key = eng.load_key(bases[:N], q=bases[N], window_bits=16)
-    a1 = orc.rand_fr_buf(rng, N).reshape(1, N, 32)
-    z_in, z_out = orc.fr_to_buf([7]), orc.fr_to_buf([orc.rand_fr(rng, 1)[0]])
+    a1 = bench.rand_fr_dev(torch, N, gen).cpu().numpy().reshape(1, N, 32)
+    z_in, z_out = fr([7]), bench.rand_fr_dev(torch, 1, gen).cpu().numpy()
     C1 = eng.commit_batch(key, a1)
     res = {"unit": "ms per call, B = 1, width 256, c = 16, host pointers"}
     res["commit"] = timeit(lambda: eng.commit_batch(key, a1))
@@ -41,8 +49,8 @@ def main():
     res["kzg_open_out_domain"] = timeit(lambda: eng.kzg_open_batch(key, a1, z_out))
     # batched verifier throughput
     B = 4096
-    a = orc.rand_fr_buf(rng, B * N).reshape(B, N, 32)
-    zb = orc.fr_to_buf([int(v) for v in rng.integers(0, N, B)])
+    a = bench.rand_fr_dev(torch, B * N, gen).cpu().numpy().reshape(B, N, 32)
+    zb = fr(rng.integers(0, N, B))
     C = eng.commit_batch(key, a)
     L, R, tip, y = eng.ipa_prove_batch(key, a, zb, C)
     ms = timeit(lambda: eng.ipa_verify_batch(key, zb, C, L, R, tip, y), reps=5)
