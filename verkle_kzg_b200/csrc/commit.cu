@@ -60,7 +60,7 @@ __device__ __forceinline__ xyzz_t shfl_xor_xyzz_c(const xyzz_t& v, int mask) {
     return r;
 }
 
-// LPJ lanes per job (32, 8 or 4): a warp runs 32 / LPJ jobs side by side, each group of LPJ lanes with its own
+// LPJ lanes per job (32, 16, 8, 4, 2 or 1): a warp runs 32 / LPJ jobs side by side, each group of LPJ lanes with its own
 // slice of the shared-memory entry list.  Wide jobs (commits, IPA cross terms) use the whole warp; verkle nodes
 // with a handful of terms use 4 or 8 lanes so that the shuffle-tree fold (log2 LPJ full additions) does not
 // dominate their few table additions.
@@ -206,6 +206,8 @@ static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scal
 int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                            uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job) {
     if (jobs == 0) return VKZG_OK;
+    if (lanes_per_job == 1) return launch_fixed_base<1>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
+    if (lanes_per_job == 2) return launch_fixed_base<2>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 8) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     // big dense batches: fewer lanes per job shorten the shuffle-tree fold (log2(lanes) full additions per job) as long as

@@ -6,55 +6,50 @@
 namespace vk {
 
 // -------------------------------------------------------------------------------------------------
-// XYZZ -> affine, K points per thread share one Fermat inversion (Montgomery's trick).
+// XYZZ -> affine, K points per thread share one inversion (Montgomery's trick).  The running prefix products are
+// parked in the x coordinate of the OUTPUT slots, so K is not limited by registers: a few points use K = 1 (latency),
+// big batches K = 32 (the binary inversion is ~40 multiplication-equivalents under warp divergence, i.e. as much as a
+// small verkle node's whole commitment if it is not shared widely).
 // -------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(128) k_normalize(const xyzz_t* __restrict__ in, uint64_t n, affine_t* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_normalize(const xyzz_t* __restrict__ in, uint64_t n, uint32_t K, affine_t* __restrict__ out) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t first = t * K;
     if (first >= n) return;
-    fp_t pre[K];
+    uint32_t cnt = (uint32_t)(n - first < K ? n - first : K);
     fp_t run = fp_one<Q>();
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        pre[j] = run;
-        if (first + j < n) {
-            fp_t z = fp_load(&in[first + j].zzz);
-            if (!fp_is_zero(z)) run = fp_mul_ni<Q>(run, z);
-        }
+#pragma unroll 1
+    for (uint32_t j = 0; j < cnt; ++j) {
+        fp_store(&out[first + j].x, run);
+        fp_t z = fp_load(&in[first + j].zzz);
+        if (!fp_is_zero(z)) run = fp_mul_ni<Q>(run, z);
     }
     fp_t inv = fp_inv<Q>(run);
-#pragma unroll
-    for (int j = K - 1; j >= 0; --j) {
-        if (first + j < n) {
-            xyzz_t p;
-            p.x = fp_load(&in[first + j].x);
-            p.y = fp_load(&in[first + j].y);
-            p.zz = fp_load(&in[first + j].zz);
-            p.zzz = fp_load(&in[first + j].zzz);
-            affine_t a = affine_inf();
-            if (!fp_is_zero(p.zzz)) {
-                fp_t zinv = fp_mul_ni<Q>(inv, pre[j]);
-                inv = fp_mul_ni<Q>(inv, p.zzz);
-                fp_t tt = fp_mul_ni<Q>(zinv, p.zz);
-                fp_t zz_inv = fp_mul_ni<Q>(tt, tt);
-                a.x = fp_mul_ni<Q>(p.x, zz_inv);
-                a.y = fp_mul_ni<Q>(p.y, zinv);
-            }
-            fp_store(&out[first + j].x, a.x);
-            fp_store(&out[first + j].y, a.y);
+#pragma unroll 1
+    for (uint32_t j = cnt; j-- > 0;) {
+        xyzz_t p;
+        p.x = fp_load(&in[first + j].x);
+        p.y = fp_load(&in[first + j].y);
+        p.zz = fp_load(&in[first + j].zz);
+        p.zzz = fp_load(&in[first + j].zzz);
+        affine_t a = affine_inf();
+        if (!fp_is_zero(p.zzz)) {
+            fp_t zinv = fp_mul_ni<Q>(inv, fp_load(&out[first + j].x));
+            inv = fp_mul_ni<Q>(inv, p.zzz);
+            fp_t tt = fp_mul_ni<Q>(zinv, p.zz);
+            fp_t zz_inv = fp_mul_ni<Q>(tt, tt);
+            a.x = fp_mul_ni<Q>(p.x, zz_inv);
+            a.y = fp_mul_ni<Q>(p.y, zinv);
         }
+        fp_store(&out[first + j].x, a.x);
+        fp_store(&out[first + j].y, a.y);
     }
 }
 
 int32_t normalize_points(vkzg_ctx* ctx, const xyzz_t* d_in, uint64_t n, affine_t* d_out) {
     if (n == 0) return VKZG_OK;
-    // few points: one inversion each (latency matters); many: four share one
-    if (n <= 4096) {
-        k_normalize<1><<<ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(d_in, n, d_out);
-    } else {
-        k_normalize<4><<<ceil_div_u64((n + 3) / 4, 128), 128, 0, ctx->stream>>>(d_in, n, d_out);
-    }
+    if ((const void*)d_in == (const void*)d_out) return VKZG_ERR_ARG;  // the output doubles as scratch
+    uint32_t K = n <= 4096 ? 1 : (n <= (1u << 17) ? 4 : (n <= (1u << 19) ? 16 : 32));
+    k_normalize<<<ceil_div_u64((n + K - 1) / K, 128), 128, 0, ctx->stream>>>(d_in, n, K, d_out);
     return launch_check(ctx);
 }
 

@@ -52,7 +52,13 @@ int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint6
     }
     // lanes per node by the level's mean number of terms (leaf-side levels have 2-3 terms, internal nodes up to 256)
     uint64_t avg_terms = n_terms / n_nodes;
-    uint32_t lpj = avg_terms <= 4 ? 4 : (avg_terms <= 48 ? 8 : 32);
+    static int lpj_small = -1;
+    if (lpj_small < 0) {
+        const char* e = getenv("VKZG_TREE_LPJ");  // tuning knob for the 2-4-term levels (1, 2 or 4 lanes per node)
+        lpj_small = e ? atoi(e) : 1;
+    }
+    uint32_t lpj = avg_terms <= 4 ? (uint32_t)lpj_small : (avg_terms <= 48 ? 8 : 32);
+    if (n_nodes < 65536 && lpj < 4) lpj = 4;  // few nodes: parallelism over lanes matters more than the fold
     VK_TRY(fixed_base_msm_csr(ctx, k, sc, 0, n_nodes, 0, 0xffffffffu, d_row_ptr, d_slot, acc, lpj));
     return normalize_points(ctx, acc, n_nodes, d_out);
 }
