@@ -83,28 +83,26 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     const bool live = vjob < jobs;
     uint64_t job = vjob;
     uint32_t term0 = 0;
-    if (split > 1) {
-        job = vjob / split;
-        uint32_t Tsub = (T + split - 1) / split;
-        term0 = (uint32_t)(vjob % split) * Tsub;
-    }
-    const uint32_t Tfull = T;
+    if (split > 1) job = vjob / split;
     // dense: job j owns scalars[j*T .. (j+1)*T), term t uses base t.  CSR (row_ptr != nullptr, verkle nodes):
     // job j owns terms [row_ptr[j], row_ptr[j+1]) and term t uses base slot[t].
     const fp_t* sc = scalars + job * T;
     const uint16_t* sl = nullptr;
-    if (split > 1) {
-        uint32_t Tsub = (T + split - 1) / split;
-        T = term0 >= T ? 0 : (T - term0 < Tsub ? T - term0 : Tsub);  // terms of this slice
-        sc += term0;
-    }
-    if (!live) T = 0;
     if (row_ptr && live) {
         uint32_t t0 = row_ptr[job];
         T = row_ptr[job + 1] - t0;
         sc = scalars + t0;
         sl = slot + t0;
     }
+    const uint32_t Tfull = T;
+    if (split > 1) {
+        uint32_t Tsub = (T + split - 1) / split;
+        term0 = (uint32_t)(vjob % split) * Tsub;
+        T = term0 >= T ? 0 : (T - term0 < Tsub ? T - term0 : Tsub);  // terms of this slice
+        sc += term0;
+        if (sl) sl += term0;
+    }
+    if (!live) T = 0;
     // ipa_m != 0: job 2p is the L cross term of proof p, job 2p+1 the R cross term of an IPA round whose
     // half length is ipa_m (see ipa.cu): term j < T-1 uses base (j / m) * 2m + (L ? m : 0) + j % m and the
     // last term the base q_row (when q_row != 0xffffffff)
@@ -202,10 +200,18 @@ static int32_t launch_fixed_base(vkzg_ctx* ctx, const Key& k, const fp_t* d_scal
     return launch_check(ctx);
 }
 
-// lanes_per_job: 0 = whole warp
+// lanes_per_job: 0 = whole warp.  csr_split > 1 (CSR only): every node's term list is sliced over that many warps.
 int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
-                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job) {
+                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job,
+                           uint32_t csr_split) {
     if (jobs == 0) return VKZG_OK;
+    if (d_row_ptr && csr_split > 1) {
+        DevBuf<xyzz_t> part;
+        VK_TRY(part.alloc(ctx, jobs * csr_split));
+        VK_TRY(launch_fixed_base<32>(ctx, k, d_scalars, T, jobs * csr_split, 0, 0xffffffffu, d_row_ptr, d_slot, csr_split, part));
+        k_sum_slices<<<ceil_div_u64(jobs * 32, 128), 128, 0, ctx->stream>>>(part, jobs, csr_split, d_out);
+        return launch_check(ctx);
+    }
     if (lanes_per_job == 1) return launch_fixed_base<1>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 2) return launch_fixed_base<2>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
@@ -241,7 +247,7 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
 
 int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                        uint32_t q_row, xyzz_t* d_out) {
-    return fixed_base_msm_csr(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, d_out, 0);
+    return fixed_base_msm_csr(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, d_out, 0, 1);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -59,7 +59,16 @@ int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint6
     }
     uint32_t lpj = avg_terms <= 4 ? (uint32_t)lpj_small : (avg_terms <= 48 ? 8 : 32);
     if (n_nodes < 65536 && lpj < 4) lpj = 4;  // few nodes: parallelism over lanes matters more than the fold
-    VK_TRY(fixed_base_msm_csr(ctx, k, sc, 0, n_nodes, 0, 0xffffffffu, d_row_ptr, d_slot, acc, lpj));
+    // a handful of wide nodes (the top of the tree: up to 256 children each): slice every node over several warps
+    uint32_t split = 1;
+    if (avg_terms >= 32 && n_nodes * 4 <= (uint64_t)ctx->sm_count * 16) {
+        split = (uint32_t)(avg_terms / 8);
+        uint64_t room = (uint64_t)ctx->sm_count * 16 / n_nodes;
+        if (split > room) split = (uint32_t)room;
+        if (split > 32) split = 32;
+        if (split < 1) split = 1;
+    }
+    VK_TRY(fixed_base_msm_csr(ctx, k, sc, 0, n_nodes, 0, 0xffffffffu, d_row_ptr, d_slot, acc, lpj, split));
     return normalize_points(ctx, acc, n_nodes, d_out);
 }
 

@@ -287,6 +287,29 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         }
         handle[id] = {level, (int32_t)levels[level].close(id)};
     }
+    // ---- internal levels: order the nodes of a level by their number of children, so that the lanes / groups of one
+    //      warp (one node each) walk term lists of similar length instead of waiting for the longest
+    for (size_t l = 2; l < levels.size(); ++l) {
+        LevelBuf& L = levels[l];
+        const size_t nn = L.owner.size();
+        if (nn < 64) continue;
+        std::vector<uint32_t> perm(nn);
+        for (size_t j = 0; j < nn; ++j) perm[j] = (uint32_t)j;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
+            return L.row_ptr[a + 1] - L.row_ptr[a] > L.row_ptr[b + 1] - L.row_ptr[b];
+        });
+        LevelBuf S;
+        S.slot.reserve(L.slot.size());
+        S.child.reserve(L.child.size());
+        S.lit.reserve(L.lit.size());
+        for (size_t j = 0; j < nn; ++j) {
+            uint32_t r = perm[j];
+            for (uint32_t t2 = L.row_ptr[r]; t2 < L.row_ptr[r + 1]; ++t2) S.term(L.slot[t2], L.child[t2], L.lit[t2]);
+            uint32_t row = S.close(L.owner[r]);
+            handle[L.owner[r]] = {(uint32_t)l, (int32_t)row};
+        }
+        L = std::move(S);
+    }
     // ---- global ids: [known commitments][level 0][level 1]...
     std::vector<uint64_t> base(levels.size(), 0);
     uint64_t total = known.size();

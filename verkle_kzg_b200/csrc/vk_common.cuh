@@ -215,7 +215,8 @@ int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint3
                        uint32_t q_row, xyzz_t* d_out);
 // CSR variant (verkle nodes): job j owns terms [row_ptr[j], row_ptr[j+1]), term t uses base slot[t]
 int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
-                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job);
+                           uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job,
+                           uint32_t csr_split);
 int32_t barycentric_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_points, uint64_t B, fp_t* d_out);
 int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                        const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,

@@ -123,6 +123,18 @@ def _flatten(root, W):
     # the root must be alone in the last level
     top = max(lv.keys())
     assert len(lv[top]) == 1
+    # internal levels: nodes ordered by their number of children (lanes of one warp then walk term lists of similar
+    # length); handles of the moved nodes are remapped
+    remap = {}
+    for L in lv:
+        if L >= 2 and len(lv[L]) >= 64:
+            order_l = sorted(range(len(lv[L])), key=lambda j: -len(lv[L][j]))
+            lv[L] = [lv[L][j] for j in order_l]
+            for new, old in enumerate(order_l):
+                remap[(L, old)] = (L, new)
+    if remap:
+        for L in lv:
+            lv[L] = [[(slot, remap.get(h, h) if h is not None else None, lit) for slot, h, lit in terms] for terms in lv[L]]
     # global ids: levels in increasing order (empty levels dropped)
     order = sorted(lv.keys())
     base, acc = {}, 0
