@@ -15,14 +15,23 @@
 
 namespace vk {
 
+// lit_raw: literals are 32-byte little-endian INTEGERS (from_le_bytes_mod_order input, any value < 2^256) instead of
+// Montgomery field elements; one product by R^2 reduces and converts them here instead of on the host
 __global__ void __launch_bounds__(128) k_tree_scalars(const int32_t* __restrict__ child, const fp_t* __restrict__ lit,
-                                                      const affine_t* __restrict__ prev, uint64_t n_terms, fp_t* __restrict__ out) {
+                                                      const affine_t* __restrict__ prev, uint64_t n_terms, bool lit_raw,
+                                                      fp_t* __restrict__ out) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_terms) return;
     int32_t c = child[t];
     fp_t r;
     if (c < 0) {
         r = fp_load_ro(lit + t);
+        if (lit_raw) {
+            fp_t r2;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r2.l[k] = S::r2(k);
+            r = fp_mul<S>(r2, r);
+        }
     } else {
         affine_t p;
         p.x = fp_load(&prev[c].x);
@@ -40,14 +49,14 @@ __global__ void __launch_bounds__(128) k_tree_scalars(const int32_t* __restrict_
 }
 
 int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint64_t n_nodes, const uint16_t* d_slot,
-                   const int32_t* d_child, const fp_t* d_lit, uint64_t n_terms, const affine_t* d_prev, affine_t* d_out) {
+                   const int32_t* d_child, const fp_t* d_lit, uint64_t n_terms, const affine_t* d_prev, affine_t* d_out, bool lit_raw) {
     if (n_nodes == 0) return VKZG_OK;
     DevBuf<fp_t> sc;
     DevBuf<xyzz_t> acc;
     VK_TRY(sc.alloc(ctx, n_terms));
     VK_TRY(acc.alloc(ctx, n_nodes));
     if (n_terms) {
-        k_tree_scalars<<<ceil_div_u64(n_terms, 128), 128, 0, ctx->stream>>>(d_child, d_lit, d_prev, n_terms, sc);
+        k_tree_scalars<<<ceil_div_u64(n_terms, 128), 128, 0, ctx->stream>>>(d_child, d_lit, d_prev, n_terms, lit_raw, sc);
         VK_TRY(launch_check(ctx));
     }
     // lanes per node by the level's mean number of terms (leaf-side levels have 2-3 terms, internal nodes up to 256)
@@ -87,7 +96,7 @@ int32_t vkzg_tree_level_dev(vkzg_ctx* ctx, uint32_t key_id, const uint32_t* d_ro
     if (n_nodes && (!d_row_ptr || !d_out)) return VKZG_ERR_ARG;
     if (n_terms && (!d_slot || !d_child || !d_lit)) return VKZG_ERR_ARG;
     return tree_level(ctx, *k, d_row_ptr, n_nodes, d_slot, d_child, (const fp_t*)d_lit, n_terms, (const affine_t*)d_prev,
-                      (affine_t*)d_out);
+                      (affine_t*)d_out, false);
 }
 
 int32_t vkzg_tree_commit_levels(vkzg_ctx* ctx, uint32_t key_id, uint32_t n_levels, const uint64_t* nodes_per_level,
@@ -125,7 +134,7 @@ int32_t vkzg_tree_commit_levels(vkzg_ctx* ctx, uint32_t key_id, uint32_t n_level
         VK_TRY(upload(ctx, d_sl, slot[l], nt));
         VK_TRY(upload(ctx, d_ch, child[l], nt));
         VK_TRY(upload(ctx, d_li, lit[l], nt));
-        VK_TRY(tree_level(ctx, *k, d_rp, nn, d_sl, d_ch, d_li, nt, all.p, all.p + off));
+        VK_TRY(tree_level(ctx, *k, d_rp, nn, d_sl, d_ch, d_li, nt, all.p, all.p + off, false));
         off += nn;
     }
     const affine_t* a = all.p + (total_nodes - 1);

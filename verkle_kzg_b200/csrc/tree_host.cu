@@ -15,7 +15,7 @@
 namespace vk {
 
 int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint64_t n_nodes, const uint16_t* d_slot,
-                   const int32_t* d_child, const fp_t* d_lit, uint64_t n_terms, const affine_t* d_prev, affine_t* d_out);
+                   const int32_t* d_child, const fp_t* d_lit, uint64_t n_terms, const affine_t* d_prev, affine_t* d_out, bool lit_raw);
 
 struct HNode {
     bool internal = true;
@@ -37,6 +37,7 @@ struct vkzg_tree {
     std::vector<vk::HNode> nodes;  // node 0 is the root
     std::vector<uint8_t> stems;    // key bytes of every extension node
     uint64_t n_keys = 0;
+    uint64_t n_commits = 0;
     const uint8_t* stem(const vk::HNode& n) const { return stems.data() + n.stem_off; }
 
     int32_t child(uint32_t id, uint8_t unit) const {
@@ -218,13 +219,34 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         return VKZG_OK;
     }
     const uint32_t W = t->ext_width;
+    // literals travel as raw little-endian integers when they fit 32 bytes (the device reduces and converts them);
+    // longer stems are reduced on the host and everything travels in Montgomery form
+    const bool raw = t->key_len <= 32;
+    auto literal = [raw](const uint8_t* b, size_t len) {
+        if (!raw) return fr_from_le_bytes(b, len);
+        fp_t v = fp_zero<S>();
+        memcpy(v.l, b, len);
+        return v;
+    };
     // ---- post-order over the dirty part: heights -> levels.  Level 0 = C1 / C2 helper vectors, 1 = extensions,
     //      >= 2 internal nodes by height.  Clean children enter as known commitments (prefix of the node array).
     std::vector<LevelBuf> levels(2);
+    if (t->n_commits == 0) {  // first (bulk) commit: every node is dirty, size the leaf-side levels once
+        const size_t nn = t->nodes.size();
+        levels[0].slot.reserve(2 * nn); levels[0].child.reserve(2 * nn); levels[0].lit.reserve(2 * nn);
+        levels[0].row_ptr.reserve(nn + 1); levels[0].owner.reserve(nn);
+        levels[1].slot.reserve(3 * nn); levels[1].child.reserve(3 * nn); levels[1].lit.reserve(3 * nn);
+        levels[1].row_ptr.reserve(nn + 1); levels[1].owner.reserve(nn);
+    }
+    ++t->n_commits;
     std::vector<affine_t> known;            // commitments of clean children referenced by dirty parents
     std::vector<std::pair<uint32_t, int32_t>> handle(t->nodes.size(), {0xffffffffu, -1});  // node -> (level, row) ; level 0xfffffffe = known
     std::vector<std::pair<uint32_t, bool>> stack{{0u, false}};
-    const fp_t one = fp_one<S>(), zero = fp_zero<S>();
+    fp_t one = fp_one<S>(), zero = fp_zero<S>();
+    if (raw) {
+        one = zero;
+        one.l[0] = 1;
+    }
     while (!stack.empty()) {
         auto [id, done] = stack.back();
         stack.pop_back();
@@ -236,33 +258,22 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         }
         if (!n.internal) {
             // node.rs:226-240: leaf idx -> slots (2 idx) % W, (2 idx + 1) % W of C1 (idx < W/2) or C2; later leaves overwrite
-            std::vector<std::pair<uint16_t, fp_t>> c1, c2;
-            auto put = [](std::vector<std::pair<uint16_t, fp_t>>& v, uint16_t s, const fp_t& x) {
-                for (auto& e : v)
-                    if (e.first == s) {
-                        e.second = x;
-                        return;
-                    }
-                v.push_back({s, x});
-            };
+            // one leaf per extension (the stem is the whole key): its two halves go to C1 or to C2
+            int32_t r1 = -1, r2 = -1;
             {
                 uint32_t idx = n.leaf_unit;
-                auto& tgt = idx < W / 2 ? c1 : c2;
-                put(tgt, (uint16_t)((2 * idx) % W), fr_from_le_bytes(n.leaf_val.data(), 16));
-                put(tgt, (uint16_t)((2 * idx + 1) % W), fr_from_le_bytes(n.leaf_val.data() + 16, 16));
-            }
-            int32_t r1 = -1, r2 = -1;
-            if (!c1.empty()) {
-                for (auto& e : c1) levels[0].term(e.first, -1, e.second);
-                r1 = (int32_t)levels[0].close(0xffffffffu);
-            }
-            if (!c2.empty()) {
-                for (auto& e : c2) levels[0].term(e.first, -1, e.second);
-                r2 = (int32_t)levels[0].close(0xffffffffu);
+                uint16_t s_lo = (uint16_t)((2 * idx) % W), s_hi = (uint16_t)((2 * idx + 1) % W);
+                if (s_lo != s_hi) levels[0].term(s_lo, -1, literal(n.leaf_val.data(), 16));  // W == 1: the later write (high) wins
+                levels[0].term(s_hi, -1, literal(n.leaf_val.data() + 16, 16));
+                int32_t row = (int32_t)levels[0].close(0xffffffffu);
+                if (idx < W / 2)
+                    r1 = row;
+                else
+                    r2 = row;
             }
             // node.rs:243-253: commit([1, stem, C1, C2]); child ids are patched to global ids below (level 0 rows)
             levels[1].term(0, -1, one);
-            levels[1].term(1, -1, fr_from_le_bytes(t->stem(n), t->key_len));
+            levels[1].term(1, -1, literal(t->stem(n), t->key_len));
             if (r1 >= 0) levels[1].term(2, -(r1 + 2), zero);  // encoded: -(row + 2) = level-0 row, resolved after layout
             if (r2 >= 0) levels[1].term(3, -(r2 + 2), zero);
             handle[id] = {1u, (int32_t)levels[1].close(id)};
@@ -341,7 +352,7 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         VK_TRY(upload(ctx, d_sl, L.slot.data(), L.slot.size()));
         VK_TRY(upload(ctx, d_ch, L.child.data(), L.child.size()));
         VK_TRY(upload(ctx, d_li, L.lit.data(), L.lit.size()));
-        VK_TRY(tree_level(ctx, *k, d_rp, nn, d_sl, d_ch, d_li, L.slot.size(), all.p, all.p + base[l]));
+        VK_TRY(tree_level(ctx, *k, d_rp, nn, d_sl, d_ch, d_li, L.slot.size(), all.p, all.p + base[l], raw));
         VK_TRY(stream_sync(ctx));  // the host vectors of this level go out of use before the next upload reuses the pool
     }
     // ---- cache the new commitments on the host
