@@ -17,6 +17,7 @@
 //                        transcript, squeeze x_k (SHA-256 XMD on the device)
 // i.e. the whole round loop runs on the device with no host round trip; outputs are canonical affine.
 #include "vk_common.cuh"
+#include "warp_util.cuh"
 
 namespace vk {
 
@@ -40,7 +41,8 @@ __device__ __forceinline__ bool canon_lt_u32(const fp_t& canon, uint32_t n) {
 // ---------------------------------------------------------------------------------------------------
 // B1: PrecomputedLagrange::compute_barycentric_coefficients (precompute.rs:72-90).  Warp per point.
 //   point < size (strict, quirk Q3): unit vector;  else b_i = ((z^size - 1)/size) w^i / (z - w^i)
-// The N inversions are one Fermat inversion per lane (lanes own i = lane, lane+32, ... and batch them).
+// The N inversions are ONE inversion per warp: lanes own i = lane, lane+32, ... and batch them, the lane products are
+// inverted together (warp_inverse_of_lane_products).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_barycentric(const fp_t* __restrict__ points, uint64_t B, uint32_t size,
                                                      const fp_t* __restrict__ omega, fp_t n_inv, fp_t* __restrict__ out) {
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(128) k_barycentric(const fp_t* __restrict__ po
         fp_store(o + i, run);
         run = fp_mul_ni<S>(run, fp_sub<S>(z, fp_load_ro(omega + i)));
     }
-    fp_t inv = fp_inv<S>(run);
+    fp_t inv = warp_inverse_of_lane_products(run);
     uint32_t cnt = size > lane ? (size - lane + 31) / 32 : 0;
     for (uint32_t k = cnt; k-- > 0;) {
         uint32_t i = lane + 32 * k;

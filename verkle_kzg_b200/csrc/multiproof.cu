@@ -12,6 +12,7 @@
 // the rows — powers of r, the segmented row sums, quotients, h, both commitments and the final opening
 // with its own round challenges — runs on the device.
 #include "vk_common.cuh"
+#include "warp_util.cuh"
 
 namespace vk {
 
@@ -122,32 +123,60 @@ __global__ void __launch_bounds__(128) k_mp_groups(const fp_t* __restrict__ part
     fp_store(total + (size_t)g * N + i, acc);
 }
 
-// g[i] = sum over groups of quotient rows
+// g[i] = sum over groups of quotient rows.  Warp per column: lanes stride over the rows, shuffle-tree sum.
 __global__ void __launch_bounds__(128) k_mp_colsum(const fp_t* __restrict__ rows, uint32_t n_rows, uint32_t N, fp_t* __restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= N) return;
     fp_t acc = fp_zero<S>();
-    for (uint32_t g = 0; g < n_rows; ++g) acc = fp_add<S>(acc, fp_load(rows + (size_t)g * N + i));
-    fp_store(out + i, acc);
+    for (uint32_t g = lane; g < n_rows; g += 32) acc = fp_add<S>(acc, fp_load(rows + (size_t)g * N + i));
+    acc = warp_sum_frw(acc);
+    if (lane == 0) fp_store(out + i, acc);
 }
 
-// inv[g] = 1 / (t - z_g)   (utils.rs:57-62 for the z that occur)
-__global__ void __launch_bounds__(64) k_mp_inv(fp_t t, const fp_t* __restrict__ zf, uint32_t n, fp_t* __restrict__ inv) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
-    fp_store(inv + g, fp_inv<S>(fp_sub<S>(t, fp_load(zf + g))));
+// inv[g] = 1 / (t - z_g)   (utils.rs:57-62 for the z that occur).  Warp per 256 elements, one inversion per warp.
+__global__ void __launch_bounds__(128) k_mp_inv(fp_t t, const fp_t* __restrict__ zf, uint32_t n, fp_t* __restrict__ inv) {
+    const uint32_t PER = 8;
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    uint32_t base = warp * 32 * PER;
+    if (base >= n) return;
+    // lane owns elements base + lane + 32 k; a zero denominator (t == z) stays zero like ark_ff::batch_inversion
+    fp_t run = fp_one<S>();
+    for (uint32_t k = 0; k < PER; ++k) {
+        uint32_t g = base + lane + 32 * k;
+        if (g < n) {
+            fp_store(inv + g, run);
+            fp_t d = fp_sub<S>(t, fp_load(zf + g));
+            if (!fp_is_zero(d)) run = fp_mul_ni<S>(run, d);
+        }
+    }
+    fp_t r = warp_inverse_of_lane_products(run);
+    for (uint32_t k = PER; k-- > 0;) {
+        uint32_t g = base + lane + 32 * k;
+        if (g < n) {
+            fp_t d = fp_sub<S>(t, fp_load(zf + g));
+            fp_t v = fp_zero<S>();
+            if (!fp_is_zero(d)) {
+                v = fp_mul_ni<S>(r, fp_load(inv + g));
+                r = fp_mul_ni<S>(r, d);
+            }
+            fp_store(inv + g, v);
+        }
+    }
 }
 
-// h[i] = sum_g inv[g] total[g][i];  hmg = h - g
+// h[i] = sum_g inv[g] total[g][i];  hmg = h - g.  Warp per column.
 __global__ void __launch_bounds__(128) k_mp_h(const fp_t* __restrict__ total, const fp_t* __restrict__ inv, uint32_t n_groups,
                                               uint32_t N, const fp_t* __restrict__ gvec, fp_t* __restrict__ h,
                                               fp_t* __restrict__ hmg) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= N) return;
     fp_t acc = fp_zero<S>();
-    for (uint32_t g = 0; g < n_groups; ++g) acc = fp_add<S>(acc, fp_mul<S>(fp_load_ro(inv + g), fp_load(total + (size_t)g * N + i)));
-    fp_store(h + i, acc);
-    fp_store(hmg + i, fp_sub<S>(acc, fp_load(gvec + i)));
+    for (uint32_t g = lane; g < n_groups; g += 32) acc = fp_add<S>(acc, fp_mul<S>(fp_load_ro(inv + g), fp_load(total + (size_t)g * N + i)));
+    acc = warp_sum_frw(acc);
+    if (lane == 0) {
+        fp_store(h + i, acc);
+        fp_store(hmg + i, fp_sub<S>(acc, fp_load(gvec + i)));
+    }
 }
 
 // out = a - b
@@ -313,7 +342,7 @@ static int32_t multiproof_prove_impl(vkzg_ctx* ctx, uint32_t key_id, int32_t sch
     VK_TRY(launch_check(ctx));
     // quotients of the group totals at their (in-domain) points, summed into g
     VK_TRY(poly_batch(ctx, *k, total, N, 0, d_zf, n_groups, quo, dy, false));
-    k_mp_colsum<<<(N + 127) / 128, 128, 0, s>>>(quo, n_groups, N, gvec);
+    k_mp_colsum<<<(N * 32 + 127) / 128, 128, 0, s>>>(quo, n_groups, N, gvec);
     VK_TRY(launch_check(ctx));
     // D = commit(g)
     VK_TRY(fixed_base_msm(ctx, *k, gvec, N, 1, 0, 0xffffffffu, acc));
@@ -323,9 +352,9 @@ static int32_t multiproof_prove_impl(vkzg_ctx* ctx, uint32_t key_id, int32_t sch
     VK_TRY(stream_sync(ctx));
     tr.append_point(hD, "D");
     fp_t t = tr.digest("t");  // multiproof.rs:152-155
-    k_mp_inv<<<ceil_div_u64(n_groups, 64), 64, 0, s>>>(t, d_zf, n_groups, inv);
+    k_mp_inv<<<ceil_div_u64(((uint64_t)n_groups + 255) / 256 * 32, 128), 128, 0, s>>>(t, d_zf, n_groups, inv);
     VK_TRY(launch_check(ctx));
-    k_mp_h<<<(N + 127) / 128, 128, 0, s>>>(total, inv, n_groups, N, gvec, h, hmg);
+    k_mp_h<<<(N * 32 + 127) / 128, 128, 0, s>>>(total, inv, n_groups, N, gvec, h, hmg);
     VK_TRY(launch_check(ctx));
     VK_TRY(fixed_base_msm(ctx, *k, h, N, 1, 0, 0xffffffffu, acc));
     VK_TRY(normalize_points(ctx, acc, 1, DE.p + 1));
@@ -407,7 +436,7 @@ int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1
     VK_TRY(Cdiff.alloc(ctx, 1));
     k_powers<<<ceil_div_u64(m, 128), 128, 0, s>>>(r, m, rpow);
     VK_TRY(launch_check(ctx));
-    k_mp_inv<<<ceil_div_u64(m, 64), 64, 0, s>>>(t, dzq, (uint32_t)m, inv);
+    k_mp_inv<<<ceil_div_u64((m + 255) / 256 * 32, 128), 128, 0, s>>>(t, dzq, (uint32_t)m, inv);
     VK_TRY(launch_check(ctx));
     VK_TRY(fr_mul_elementwise(ctx, rpow, inv, m, rpow));
     VK_TRY(var_base_msm(ctx, dC, rpow, m, dE));

@@ -11,6 +11,7 @@
 // the key's precompute has size N with domain next_pow2(N).  The reference indexes out of bounds unless
 // Dn <= N, so that is required here.
 #include "vk_common.cuh"
+#include "warp_util.cuh"
 
 namespace vk {
 
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128) k_poly(PolyArgs A) {
             fp_store(row + i, run);
             run = fp_mul_ni<S>(run, fp_sub<S>(z, fp_load_ro(A.wK + i)));
         }
-        fp_t inv = fp_inv<S>(run);
+        fp_t inv = warp_inverse_of_lane_products(run);
         fp_t acc = fp_zero<S>();
         uint32_t cnt = A.len > lane ? (A.len - lane + 31) / 32 : 0;
         for (uint32_t k = cnt; k-- > 0;) {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128) k_poly(PolyArgs A) {
             fp_t d = fp_sub<S>(fp_load_ro(A.wD + i), z);
             if (!fp_is_zero(d)) run = fp_mul_ni<S>(run, d);
         }
-        fp_t inv = fp_inv<S>(run);
+        fp_t inv = warp_inverse_of_lane_products(run);
         uint32_t cnt = A.Dn > lane ? (A.Dn - lane + 31) / 32 : 0;
         for (uint32_t k = cnt; k-- > 0;) {
             uint32_t i = lane + 32 * k;
