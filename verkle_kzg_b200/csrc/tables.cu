@@ -2,20 +2,21 @@
 // multiples used by the shared-bucket Pippenger MSM, domain constants, and the batched XYZZ -> affine
 // normalisation every point result goes through.
 #include "vk_common.cuh"
+#include "warp_util.cuh"
 
 namespace vk {
 
 // -------------------------------------------------------------------------------------------------
-// XYZZ -> affine, K points per thread share one inversion (Montgomery's trick).  The running prefix products are
-// parked in the x coordinate of the OUTPUT slots, so K is not limited by registers: a few points use K = 1 (latency),
-// big batches K = 32 (the binary inversion is ~40 multiplication-equivalents under warp divergence, i.e. as much as a
-// small verkle node's whole commitment if it is not shared widely).
+// XYZZ -> affine by Montgomery's trick: every lane multiplies the zzz of its K points (prefix products parked in the x
+// coordinate of the OUTPUT slots), the 32 lane products are inverted together with ONE inversion per warp
+// (warp_inverse_of_lane_products_t: all lanes invert the same grand total, so the data-dependent binary inversion runs
+// without divergence), i.e. 32 K points share one inversion.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_normalize(const xyzz_t* __restrict__ in, uint64_t n, uint32_t K, affine_t* __restrict__ out) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t first = t * K;
-    if (first >= n) return;
-    uint32_t cnt = (uint32_t)(n - first < K ? n - first : K);
+    // (no early return: the warp-wide inversion below needs all 32 lanes; lanes past the end carry the product 1)
+    uint32_t cnt = first >= n ? 0 : (uint32_t)(n - first < K ? n - first : K);
     fp_t run = fp_one<Q>();
 #pragma unroll 1
     for (uint32_t j = 0; j < cnt; ++j) {
@@ -23,7 +24,8 @@ __global__ void __launch_bounds__(128) k_normalize(const xyzz_t* __restrict__ in
         fp_t z = fp_load(&in[first + j].zzz);
         if (!fp_is_zero(z)) run = fp_mul_ni<Q>(run, z);
     }
-    fp_t inv = fp_inv<Q>(run);
+    // one inversion per warp, on a value all lanes share (uniform control flow), instead of 32 divergent ones
+    fp_t inv = warp_inverse_of_lane_products_t<Q>(run);
 #pragma unroll 1
     for (uint32_t j = cnt; j-- > 0;) {
         xyzz_t p;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) k_normalize(const xyzz_t* __restrict__ in
 int32_t normalize_points(vkzg_ctx* ctx, const xyzz_t* d_in, uint64_t n, affine_t* d_out) {
     if (n == 0) return VKZG_OK;
     if ((const void*)d_in == (const void*)d_out) return VKZG_ERR_ARG;  // the output doubles as scratch
-    uint32_t K = n <= 4096 ? 1 : (n <= (1u << 17) ? 4 : (n <= (1u << 19) ? 16 : 32));
+    uint32_t K = n <= (1u << 16) ? 1 : (n <= (1u << 19) ? 4 : 8);
     k_normalize<<<ceil_div_u64((n + K - 1) / K, 128), 128, 0, ctx->stream>>>(d_in, n, K, d_out);
     return launch_check(ctx);
 }

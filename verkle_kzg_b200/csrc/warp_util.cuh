@@ -38,20 +38,22 @@ __device__ __forceinline__ fp_t warp_sum_frw(fp_t v) {
 // prefix and suffix products over the lanes by shuffle scans, then every lane inverts the SAME grand total (uniform
 // control flow — the binary inversion is several times slower when 32 lanes run it on 32 different values).
 // All 32 lanes must call it.
-static __device__ __noinline__ fp_t warp_inverse_of_lane_products(const fp_t t) {
+template <class F>
+static __device__ __noinline__ fp_t warp_inverse_of_lane_products_t(const fp_t t) {
     const int lane = threadIdx.x & 31;
     fp_t P = t, X = t;
 #pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         fp_t up = shfl_up_fp(P, d), dn = shfl_down_fp(X, d);
-        if (lane >= d) P = fp_mul_ni<S>(P, up);
-        if (lane + d < 32) X = fp_mul_ni<S>(X, dn);
+        if (lane >= d) P = fp_mul_ni<F>(P, up);
+        if (lane + d < 32) X = fp_mul_ni<F>(X, dn);
     }
-    fp_t inv = fp_inv<S>(shfl_fp(P, 31));
+    fp_t inv = fp_inv<F>(shfl_fp(P, 31));
     fp_t left = shfl_up_fp(P, 1), right = shfl_down_fp(X, 1);
-    if (lane > 0) inv = fp_mul_ni<S>(inv, left);
-    if (lane < 31) inv = fp_mul_ni<S>(inv, right);
+    if (lane > 0) inv = fp_mul_ni<F>(inv, left);
+    if (lane < 31) inv = fp_mul_ni<F>(inv, right);
     return inv;
 }
+static __device__ __forceinline__ fp_t warp_inverse_of_lane_products(const fp_t t) { return warp_inverse_of_lane_products_t<S>(t); }
 
 }  // namespace vk
