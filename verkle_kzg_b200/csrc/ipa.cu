@@ -206,11 +206,16 @@ __global__ void __launch_bounds__(128) k_ipa_fold_scalars(IpaState st, uint64_t 
 __global__ void __launch_bounds__(64) k_ipa_challenge(IpaState st, uint64_t B, uint32_t round, uint32_t rounds,
                                                       affine_t* __restrict__ L_out, affine_t* __restrict__ R_out) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
-    xyzz_t l = st.lr[2 * p], r = st.lr[2 * p + 1];
+    const bool live = p < B;  // (no early return before the warp-wide inversion)
+    xyzz_t l = xyzz_inf(), r = xyzz_inf();
+    if (live) {
+        l = st.lr[2 * p];
+        r = st.lr[2 * p + 1];
+    }
     bool linf = xyzz_is_inf(l), rinf = xyzz_is_inf(r);
     fp_t zl = linf ? fp_one<Q>() : l.zzz, zr = rinf ? fp_one<Q>() : r.zzz;
-    fp_t inv = fp_inv<Q>(fp_mul_ni<Q>(zl, zr));
+    fp_t inv = warp_inverse_of_lane_products_t<Q>(fp_mul_ni<Q>(zl, zr));  // the 64 points of a warp share one inversion
+    if (!live) return;
     affine_t la = linf ? affine_inf() : xyzz_to_affine_with_inv(l, fp_mul_ni<Q>(inv, zr));
     affine_t ra = rinf ? affine_inf() : xyzz_to_affine_with_inv(r, fp_mul_ni<Q>(inv, zl));
     L_out[p * rounds + round] = la;

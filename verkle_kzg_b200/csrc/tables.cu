@@ -78,15 +78,16 @@ __global__ void __launch_bounds__(128) k_wtab_level(affine_t* __restrict__ table
     const uint32_t g = per < (uint32_t)G ? per : (uint32_t)G;
     const uint32_t groups = per / g;
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)rows * groups) return;
-    uint32_t row = (uint32_t)(t / groups), grp = (uint32_t)(t % groups);
+    const bool live = t < (uint64_t)rows * groups;  // (no early return: the warp-wide inversion needs all 32 lanes)
+    uint32_t row = live ? (uint32_t)(t / groups) : 0, grp = live ? (uint32_t)(t % groups) : 0;
     affine_t* T = table + ((size_t)row << (c - 1));
     affine_t Bp = T[per - 1];
     bool binf = affine_is_inf(Bp);
     fp_t pre[G];
     fp_t run = fp_one<Q>();
+    const uint32_t gg = live ? g : 0;
 #pragma unroll 1
-    for (uint32_t j = 0; j < g; ++j) {
+    for (uint32_t j = 0; j < gg; ++j) {
         uint32_t idx = grp * g + j;
         pre[j] = run;
         fp_t den;
@@ -98,9 +99,9 @@ __global__ void __launch_bounds__(128) k_wtab_level(affine_t* __restrict__ table
             den = fp_sub<Q>(Bp.x, fp_load(&T[idx].x));
         run = fp_mul_ni<Q>(run, den);
     }
-    fp_t inv = fp_inv<Q>(run);
+    fp_t inv = warp_inverse_of_lane_products_t<Q>(run);  // 32 x G additions share one inversion
 #pragma unroll 1
-    for (int j = (int)g - 1; j >= 0; --j) {
+    for (int j = (int)gg - 1; j >= 0; --j) {
         uint32_t idx = grp * g + j;
         affine_t r = affine_inf();
         if (!binf) {
