@@ -402,7 +402,10 @@ def run_native(args):
         per = n // world                                                        # point-range sharding (configs[3])
         gen.manual_seed(0x5EED0004 + rank)
         bases = make_points_dev(torch, eng, per, gen)
+        t_key = time.perf_counter()
         key = eng.load_key_dev(bases, per, kind=_lib.KEY_MSM)
+        extra["key_load_s"] = round(time.perf_counter() - t_key, 2)
+        extra["msm_table_gb"] = round(key.table_bytes / 1e9, 2)
         s = rand_fr_dev(torch, per, gen)
         part = torch.empty((1, 64), dtype=torch.uint8, device="cuda")
         allp = torch.empty((world, 64), dtype=torch.uint8, device="cuda")

@@ -151,30 +151,31 @@ int32_t build_window_tables(vkzg_ctx* ctx, Key& k) {
 // MSM tables: table[w * n + i] = 2^(c w) * base_i
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_mtab(const affine_t* __restrict__ bases, uint32_t n, uint32_t W, uint32_t c,
-                                              affine_t* __restrict__ table) {
+                                              xyzz_t* __restrict__ tmp) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     affine_t P;
     P.x = fp_load(&bases[i].x);
     P.y = fp_load(&bases[i].y);
-    fp_store(&table[i].x, P.x);
-    fp_store(&table[i].y, P.y);
     xyzz_t acc = xyzz_from_affine(P);
+    tmp[i] = acc;
 #pragma unroll 1
     for (uint32_t w = 1; w < W; ++w) {
 #pragma unroll 1
         for (uint32_t b = 0; b < c; ++b) acc = xyzz_dbl_ni(acc);
-        affine_t a = xyzz_to_affine(acc);
-        fp_store(&table[(size_t)w * n + i].x, a.x);
-        fp_store(&table[(size_t)w * n + i].y, a.y);
+        tmp[(size_t)w * n + i] = acc;
     }
 }
 
 int32_t build_msm_tables(vkzg_ctx* ctx, Key& k) {
     k.table_points = (uint64_t)k.n * k.W;
     VK_CUDA(cudaMalloc((void**)&k.table, k.table_points * sizeof(affine_t)));
-    k_mtab<<<ceil_div_u64(k.n, 128), 128, 0, ctx->stream>>>(k.bases, k.n, k.W, k.c, k.table);
-    return launch_check(ctx);
+    // doubling chains in XYZZ, then ONE batched normalisation of all n * W points (shared inversions)
+    DevBuf<xyzz_t> tmp;
+    VK_TRY(tmp.alloc(ctx, k.table_points));
+    k_mtab<<<ceil_div_u64(k.n, 128), 128, 0, ctx->stream>>>(k.bases, k.n, k.W, k.c, tmp);
+    VK_TRY(launch_check(ctx));
+    return normalize_points(ctx, tmp, k.table_points, k.table);
 }
 
 // -------------------------------------------------------------------------------------------------
