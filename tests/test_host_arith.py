@@ -44,7 +44,7 @@ def test_field_ops(hc, tag, mod):
     assert dec(_op(hc, tag, 1, a, b)) == [(x - y) % mod for x, y in zip(xs, ys)]
     assert dec(_op(hc, tag, 2, a, b)) == [(x * y) % mod for x, y in zip(xs, ys)]
     assert dec(_op(hc, tag, 6, a)) == [(-x) % mod for x in xs]
-    nz = [x for x in xs[:40] + edge if x]
+    nz = [x for x in xs[:400] + edge + [3, 5, (mod - 1) // 3, 1 << 200, (1 << 253) + 12345] if x]
     assert dec(_op(hc, tag, 3, enc(nz))) == [pow(x, -1, mod) for x in nz]
     assert dec(_op(hc, tag, 7, enc(nz))) == [pow(x, -1, mod) for x in nz]
     assert dec(_op(hc, tag, 3, enc([0]))) == [0]
