@@ -117,6 +117,11 @@ int32_t vkzg_evaluate_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, ui
 int32_t vkzg_quotient_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n,
                             const vkzg_fr* points, uint64_t B, vkzg_fr* out, vkzg_fr* y);
 
+int32_t vkzg_evaluate_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
+                                const vkzg_fr* d_points, uint64_t B, vkzg_fr* d_y);
+int32_t vkzg_quotient_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
+                                const vkzg_fr* d_points, uint64_t B, vkzg_fr* d_out, vkzg_fr* d_y);
+
 /* ---- K3: KZG::prove_point (kzg/mod.rs:136-154), batched over B openings ------------------------------ */
 int32_t vkzg_kzg_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f /*[B][len]*/, uint32_t len, uint32_t domain_n,
                             const vkzg_fr* points /*[B]*/, uint64_t B, vkzg_g1_affine* proof /*[B]*/, vkzg_fr* y /*[B]*/);

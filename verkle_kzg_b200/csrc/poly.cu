@@ -306,6 +306,22 @@ int32_t vkzg_quotient_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, ui
     return stream_sync(ctx);
 }
 
+// device-pointer variants (rows that hit the reference's panic get a zero quotient; no status)
+int32_t vkzg_quotient_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
+                                const vkzg_fr* d_points, uint64_t B, vkzg_fr* d_out, vkzg_fr* d_y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!d_f || !d_points || !d_out || !d_y))) return VKZG_ERR_ARG;
+    return poly_batch(ctx, *k, (const fp_t*)d_f, len, domain_n, (const fp_t*)d_points, B, (fp_t*)d_out, (fp_t*)d_y, false);
+}
+int32_t vkzg_evaluate_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
+                                const vkzg_fr* d_points, uint64_t B, vkzg_fr* d_y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!d_f || !d_points || !d_y))) return VKZG_ERR_ARG;
+    return poly_batch(ctx, *k, (const fp_t*)d_f, len, domain_n, (const fp_t*)d_points, B, nullptr, (fp_t*)d_y, false);
+}
+
 int32_t vkzg_kzg_open_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
                                 const vkzg_fr* d_points, uint64_t B, vkzg_g1_affine* d_proof, vkzg_fr* d_y) {
     VK_TRY(ctx_check(ctx));

@@ -254,6 +254,14 @@ class Engine:
                                           hptr(points), ctypes.c_uint64(B), hptr(q), hptr(y)), "vkzg_quotient_batch")
         return q, y
 
+    def quotient_batch_dev(self, key, d_f, ln, d_points, B, d_q, d_y, domain_n=0):
+        check(self._L.vkzg_quotient_batch_dev(self._ctx, ctypes.c_uint32(key.id), dptr(d_f), ctypes.c_uint32(ln), ctypes.c_uint32(domain_n),
+                                              dptr(d_points), ctypes.c_uint64(B), dptr(d_q), dptr(d_y)), "vkzg_quotient_batch_dev")
+
+    def evaluate_batch_dev(self, key, d_f, ln, d_points, B, d_y, domain_n=0):
+        check(self._L.vkzg_evaluate_batch_dev(self._ctx, ctypes.c_uint32(key.id), dptr(d_f), ctypes.c_uint32(ln), ctypes.c_uint32(domain_n),
+                                              dptr(d_points), ctypes.c_uint64(B), dptr(d_y)), "vkzg_evaluate_batch_dev")
+
     def kzg_open_batch(self, key, f, points, domain_n=0):
         f = u8(f, 32)
         B, ln = f.shape[0], f.shape[1]
