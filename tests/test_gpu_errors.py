@@ -1,0 +1,67 @@
+"""Error behaviour of the C ABI on the GPU: status codes instead of crashes for bad arguments, wrong key kinds and
+shapes the reference itself rejects or panics on."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from verkle_kzg_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_status_codes(eng):
+    from verkle_kzg_b200 import VkzgError, _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(1)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, 9)
+    wkey = eng.load_key(bases[:8], q=bases[8], window_bits=8)
+    kkey = eng.load_key(bases[:8], window_bits=8)           # no q: a KZG-style key
+    mkey = eng.load_key(bases[:8], kind=2, window_bits=8)
+    s = orc.rand_fr_buf(rng, 8).reshape(1, 8, 32)
+    out = np.zeros((1, 64), dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    # unknown key id, null pointers
+    assert L.vkzg_commit_batch(eng._ctx, ctypes.c_uint32(9999), p(s), ctypes.c_uint32(8), ctypes.c_uint64(1), p(out)) == -2
+    assert L.vkzg_commit_batch(eng._ctx, ctypes.c_uint32(wkey.id), None, ctypes.c_uint32(8), ctypes.c_uint64(1), p(out)) == -2
+    assert L.vkzg_commit_batch(None, ctypes.c_uint32(wkey.id), p(s), ctypes.c_uint32(8), ctypes.c_uint64(1), p(out)) == -2
+    # wrong key kind for the entry point
+    with pytest.raises(VkzgError) as e1:
+        eng.commit_batch(mkey, s)
+    assert e1.value.status == -2
+    with pytest.raises(VkzgError) as e2:
+        eng.msm(wkey, s[0])
+    assert e2.value.status == -2
+    # IPA needs q: a key without it refuses to prove / verify
+    C = eng.commit_batch(kkey, s)
+    with pytest.raises(VkzgError):
+        eng.ipa_prove_batch(kkey, s, orc.fr_to_buf([1]), C)
+    # width 0 and width beyond the key
+    assert L.vkzg_commit_batch(eng._ctx, ctypes.c_uint32(wkey.id), p(s), ctypes.c_uint32(0), ctypes.c_uint64(1), p(out)) == -3
+    assert L.vkzg_commit_batch(eng._ctx, ctypes.c_uint32(wkey.id), p(s), ctypes.c_uint32(9), ctypes.c_uint64(1), p(out)) == -3
+    # bad window width / key kind at load
+    kid = ctypes.c_uint32(0)
+    assert L.vkzg_key_load(eng._ctx, p(bases), ctypes.c_uint32(8), None, ctypes.c_uint32(1), ctypes.c_uint32(21), ctypes.byref(kid)) == -2
+    assert L.vkzg_key_load(eng._ctx, p(bases), ctypes.c_uint32(8), None, ctypes.c_uint32(7), ctypes.c_uint32(0), ctypes.byref(kid)) == -2
+    assert L.vkzg_key_load(eng._ctx, p(bases), ctypes.c_uint32(8), p(bases[8:]), ctypes.c_uint32(2), ctypes.c_uint32(0), ctypes.byref(kid)) == -2
+    # multiproof: z outside the key, empty query list
+    f = orc.rand_fr_buf(rng, 2 * 8).reshape(2, 8, 32)
+    Cq = eng.commit_batch(wkey, f)
+    with pytest.raises(VkzgError) as e3:
+        eng.multiproof_prove(wkey, "ipa", f, Cq, np.array([0, 8], dtype=np.uint64), f[:, 0])
+    assert e3.value.status == -3
+    # everything still works after the errors
+    assert (eng.commit_batch(wkey, s) == orc.commit_batch(bases[:8], s)).all()
+    for k in (wkey, kkey, mkey):
+        k.free()
+    with pytest.raises(VkzgError):
+        eng.commit_batch(wkey, s)                             # freed key
