@@ -517,8 +517,10 @@ def run_native(args):
         madds_per_unit = terms * WINDOWS / max(1, int(sel.sum()))               # upper bound: zero digits are skipped at run time
         launches_timed = len(levels)
         units_per_step = int(sel.sum())
-        h2d = sum(lv["row_ptr"].nbytes + lv["slot"].nbytes + lv["child"].nbytes + lv["lit"].nbytes for lv in levels)
-        d2h = 64
+        # e2e traffic of vkzg_tree_commit: extensions travel compact (32-byte stem + unit + 32-byte value; the device writes
+        # their CSR rows), internal levels as row_ptr + (slot, child) per term; every node commitment is cached back
+        h2d = counts[1] * 65 + sum(4 * (c + 1) + 6 * len(lv["slot"]) for lv, c in zip(levels[2:], counts[2:]))
+        d2h = 64 * sum(counts[1:])
         metric, unit = "verkle_tree_commit_keys_per_s", "keys/s"
         cfg = {"workload": f"configs[4]: verkle tree of {nkeys} random 32-byte keys, every node recommitted level by level up to the root",
                "keys_this_rank": units_per_step, "nodes_per_level": counts, "terms": terms, "host_flatten_seconds_not_timed": round(host_build_s, 1)}
@@ -539,13 +541,13 @@ def run_native(args):
     # ---- the dominant kernel's own launch durations (roofline): every launch bracketed by a CUDA event pair on its stream.
     #      Taken in a second pass of K steps with the IPA half-batches on ONE stream, so that a bracket times one kernel alone
     #      (in the timed region above the two half-batches interleave on two streams and brackets would overlap).
-    eng.set_option(1, 0)
+    eng.set_option(eng.OPT_IPA_TWO_STREAMS, 0)
     step()
     eng.kernel_timing(True)
     ms_k, _ = timed_steps(torch, dist, world, step, args.steps, 0)
     kn, kms = eng.kernel_timing_read()
     eng.kernel_timing(False)
-    eng.set_option(1, 1)
+    eng.set_option(eng.OPT_IPA_TWO_STREAMS, 1)
     if world > 1:
         tu = torch.tensor([units_per_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(tu)
@@ -564,6 +566,22 @@ def run_native(args):
         return
     macs_per_launch_set = units_per_step * madds_per_unit * FQ_MUL_PER_MADD * MAC32_PER_FQ_MUL
     achieved = macs_per_launch_set * args.steps / (kms * 1e-3) / 1e12 if kms > 0 else None
+    # The same kernel against the HBM roofline (algorithmic bytes = one 64-byte table point per addition): the gather
+    # stream is a few per cent of the measured copy bandwidth, i.e. the kernel is not memory-bound.
+    hbm_peak, hbm_src = measured_hbm_peak()
+    hbm_view = None
+    if kn and kms:
+        gbs = (units_per_step * madds_per_unit * args.steps) * 64.0 / (kms * 1e-3) / 1e9
+        hbm_view = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}
+    # SURVEY.md section 8d's per-unit figures (8-bit windows, Jacobian 11-mul additions): the work the REFERENCE algorithm
+    # would need, not what this kernel executes (wider windows need fewer additions), so its "frac" can exceed 1.
+    survey_mac = {"ipa": 12.3e6 + 98.9e6, "commit": 12.3e6, "kzg": 12.3e6 + 0.17e6,
+                  "msm": {16: 35.4e3, 18: 31.0e3, 20: 26.1e3}.get(getattr(args, "log2n", 20))}.get(wl)
+    survey_acct = None
+    if survey_mac and kms:
+        a = units_per_step * survey_mac * args.steps / (kms * 1e-3) / 1e12
+        survey_acct = {"mac32_per_unit": survey_mac, "achieved": a, "frac": a / peak if peak else None,
+                       "note": "reference-algorithm work per unit; > 1 means fewer operations were executed than that algorithm needs"}
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if wl in ("msm", "tree") else "weak", "vs_baseline": None,
@@ -571,11 +589,13 @@ def run_native(args):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": {
-            "bound": "int32-pipe (IMAD); big-integer modular arithmetic, neither hbm nor tensor",
+            "bound": "int32",
+            "bound_note": "integer multiply pipe (IMAD): 254-bit modular arithmetic is neither hbm- nor tensor-bound; the hbm view of the same kernel is under hbm_view",
             "kernel": "k_msm_bucket" if wl == "msm" else "k_fixed_base_msm",
             "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": "measured live: dependency-free mad.wide.u32 chains on all SMs (vkzg_probe_imad_dev); MEASURED_PEAKS.json has no integer figure",
             "work_model": f"{madds_per_unit} mixed additions per unit x {FQ_MUL_PER_MADD} Fq-mul x {MAC32_PER_FQ_MUL} MAC32",
+            "survey_accounting": survey_acct,
             "kernel_launches_timed": kn, "kernel_ms_total": kms, "kernel_share_of_step": kms / ms_k if ms_k else None,
             "one_stream_ms_per_step": ms_k / args.steps,
             # DRAM bytes per launch: 128 B per table addition as ncu measured it on this kernel (dram__bytes_read.sum +
@@ -583,6 +603,7 @@ def run_native(args):
             # launch of 13.7 M additions; every 64-byte point is fetched at 128-byte granularity) x additions per launch
             "traffic": (units_per_step * madds_per_unit * args.steps / kn) * 128.0 if kn else None,
             "algorithmic_bytes_per_launch": (units_per_step * madds_per_unit * args.steps / kn) * 64.0 if kn else None,
+            "hbm_view": hbm_view,
             "ncu": "sm__pipe_fmaheavy_cycles_active 85 % (k_fixed_base_msm), 86 % (k_msm_bucket); DRAM read ~10 % of peak (profiles/)",
         },
     }
@@ -605,6 +626,15 @@ def run_native(args):
 
 
 _REAL_STDOUT = None
+
+
+def measured_hbm_peak():
+    """HBM copy bandwidth from the driver-written MEASURED_PEAKS.json, else B200_PROFILING.md's fallback."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
 def emit(line):

@@ -57,8 +57,11 @@ int32_t vkzg_ctx_create_on_stream(vkzg_ctx** out, int32_t device_id, void* cuda_
 int32_t vkzg_ctx_destroy(vkzg_ctx* ctx);
 int32_t vkzg_ctx_sync(vkzg_ctx* ctx);
 /* options: VKZG_OPT_IPA_TWO_STREAMS (default 1): batches of >= 8192 IPA proofs run as two half-batches on two streams so
- * that one half's latency-bound challenge / fold kernels hide under the other half's MSM kernel                      */
-enum { VKZG_OPT_IPA_TWO_STREAMS = 1 };
+ * that one half's latency-bound challenge / fold kernels hide under the other half's MSM kernel.
+ * VKZG_OPT_TREE_FLATTEN (default 0 = automatic): how vkzg_tree_commit gathers the dirty nodes — 1 = always the sequential
+ * bulk pass over the node array, 2 = always the depth-first walk of the dirty paths (automatic: bulk when more than an
+ * eighth of the nodes is dirty).  Results are identical; the knob exists for tests and measurements.                */
+enum { VKZG_OPT_IPA_TWO_STREAMS = 1, VKZG_OPT_TREE_FLATTEN = 2 };
 int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 uint64_t vkzg_ctx_launches(const vkzg_ctx* ctx);

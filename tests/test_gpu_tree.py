@@ -71,10 +71,14 @@ def test_empty_tree(eng, key256):
     assert not VerkleTree(32, 256).commitment(eng, key).any()
 
 
-@pytest.mark.parametrize("n,key_len,width,low_entropy", [(1, 32, 256, False), (300, 32, 256, True), (500, 4, 256, True), (200, 32, 32, False)])
-def test_native_tree_incremental_commit(eng, key256, n, key_len, width, low_entropy):
+@pytest.mark.parametrize("n,key_len,width,low_entropy", [(1, 32, 256, False), (300, 32, 256, True), (500, 4, 256, True), (200, 32, 32, False),
+                                                          (150, 40, 256, True),    # stems longer than 32 bytes: host-reduced literals
+                                                          (120, 32, 1, False), (120, 32, 2, False), (120, 32, 5, False)])  # narrow extension layouts
+@pytest.mark.parametrize("flatten", [0, 1, 2])   # automatic / bulk pass / depth-first walk of the dirty paths
+def test_native_tree_incremental_commit(eng, key256, n, key_len, width, low_entropy, flatten):
     """libvkzg's native host tree: full commit, then incremental recommits of only the dirty paths, all equal to the oracle"""
     from verkle_kzg_b200.tree import NativeVerkleTree
+    eng.set_option(eng.OPT_TREE_FLATTEN, flatten)
     bases, key = key256
     rng = np.random.default_rng(n * 3 + key_len)
     hi = 4 if low_entropy else 256
@@ -104,3 +108,4 @@ def test_native_tree_incremental_commit(eng, key256, n, key_len, width, low_entr
     if m > 100:
         assert t.last_committed < full
     t.close()
+    eng.set_option(eng.OPT_TREE_FLATTEN, 0)

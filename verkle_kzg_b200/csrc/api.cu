@@ -72,6 +72,8 @@ int32_t vkzg_ctx_destroy(vkzg_ctx* ctx) {
         cudaFree(kv.second.dom.omega);
     }
     for (auto& kv : ctx->domains) cudaFree(kv.second.omega);
+    for (void* h : ctx->host_stage)
+        if (h) cudaFreeHost(h);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -91,6 +93,10 @@ int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value) {
     VK_TRY(ctx_check(ctx));
     switch (option) {
         case VKZG_OPT_IPA_TWO_STREAMS: ctx->ipa_two_streams = value != 0; return VKZG_OK;
+        case VKZG_OPT_TREE_FLATTEN:
+            if (value < 0 || value > 2) return VKZG_ERR_ARG;
+            ctx->tree_flatten = value;
+            return VKZG_OK;
         default: return VKZG_ERR_ARG;
     }
 }

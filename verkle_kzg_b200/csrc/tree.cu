@@ -81,6 +81,71 @@ int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint6
     return normalize_points(ctx, acc, n_nodes, d_out);
 }
 
+// Extension nodes in compact form (one stem, one leaf unit, one 32-byte value each; the stem is the whole key, so every
+// extension of the reference holds exactly one leaf, node.rs:173-177) -> the CSR rows of the two leaf-side levels:
+//   level 0, row j: the C1 / C2 helper vector (node.rs:226-240): value halves at slots (2 idx) % W and (2 idx + 1) % W
+//   level 1, row j: commit([1, stem, C1, C2]) (node.rs:243-253) with only the helper that exists (C1 iff idx < W/2)
+// Literals are raw little-endian integers (k_tree_scalars converts them).  T0 = terms per level-0 row (1 iff W == 1:
+// both halves land on slot 0 and the later write, the high half, wins).
+__global__ void __launch_bounds__(128) k_tree_ext_expand(const fp_t* __restrict__ stem, const uint8_t* __restrict__ unit,
+                                                         const uint4* __restrict__ val, uint64_t n, uint32_t W, int32_t base0,
+                                                         uint32_t* __restrict__ rp0, uint16_t* __restrict__ slot0,
+                                                         int32_t* __restrict__ child0, fp_t* __restrict__ lit0,
+                                                         uint32_t* __restrict__ rp1, uint16_t* __restrict__ slot1,
+                                                         int32_t* __restrict__ child1, fp_t* __restrict__ lit1) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n) return;
+    const uint32_t T0 = W == 1 ? 1u : 2u;
+    rp0[j] = (uint32_t)(T0 * j);
+    rp1[j] = (uint32_t)(3 * j);
+    if (j == n) return;
+    uint32_t idx = unit[j];
+    uint4 lo = val[2 * j], hi = val[2 * j + 1];
+    fp_t v = fp_zero<S>();
+    uint64_t t = T0 * j;
+    if (T0 == 2) {
+        v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+        slot0[t] = (uint16_t)((2 * idx) % W);
+        child0[t] = -1;
+        fp_store(lit0 + t, v);
+        ++t;
+    }
+    v.l[0] = hi.x; v.l[1] = hi.y; v.l[2] = hi.z; v.l[3] = hi.w;
+    slot0[t] = (uint16_t)((2 * idx + 1) % W);
+    child0[t] = -1;
+    fp_store(lit0 + t, v);
+    t = 3 * j;
+    v = fp_zero<S>();
+    v.l[0] = 1;
+    slot1[t] = 0; child1[t] = -1; fp_store(lit1 + t, v);
+    slot1[t + 1] = 1; child1[t + 1] = -1; fp_store(lit1 + t + 1, fp_load_ro(stem + j));
+    slot1[t + 2] = idx < W / 2 ? 2 : 3; child1[t + 2] = base0 + (int32_t)j;  // lit1 unused for child terms
+}
+
+// all[base0 .. base0+n) <- helper commitments, all[base1 .. base1+n) <- extension commitments
+int32_t tree_ext_levels(vkzg_ctx* ctx, const Key& k, const fp_t* d_stem, const uint8_t* d_unit, const uint8_t* d_val, uint64_t n,
+                        uint32_t W, affine_t* d_all, uint64_t base0, uint64_t base1) {
+    if (n == 0) return VKZG_OK;
+    const uint64_t T0 = W == 1 ? 1 : 2;
+    DevBuf<uint32_t> rp0, rp1;
+    DevBuf<uint16_t> sl0, sl1;
+    DevBuf<int32_t> ch0, ch1;
+    DevBuf<fp_t> li0, li1;
+    VK_TRY(rp0.alloc(ctx, n + 1));
+    VK_TRY(rp1.alloc(ctx, n + 1));
+    VK_TRY(sl0.alloc(ctx, T0 * n));
+    VK_TRY(ch0.alloc(ctx, T0 * n));
+    VK_TRY(li0.alloc(ctx, T0 * n));
+    VK_TRY(sl1.alloc(ctx, 3 * n));
+    VK_TRY(ch1.alloc(ctx, 3 * n));
+    VK_TRY(li1.alloc(ctx, 3 * n));
+    k_tree_ext_expand<<<ceil_div_u64(n + 1, 128), 128, 0, ctx->stream>>>(d_stem, d_unit, (const uint4*)d_val, n, W, (int32_t)base0, rp0, sl0,
+                                                                         ch0, li0, rp1, sl1, ch1, li1);
+    VK_TRY(launch_check(ctx));
+    VK_TRY(tree_level(ctx, k, rp0, n, sl0, ch0, li0, T0 * n, d_all, d_all + base0, true));
+    return tree_level(ctx, k, rp1, n, sl1, ch1, li1, 3 * n, d_all, d_all + base1, true);
+}
+
 }  // namespace vk
 
 using namespace vk;

@@ -9,6 +9,9 @@
 // k_fixed_base_msm in CSR mode), feeding clean children in as already-known commitments.
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "vk_common.cuh"
 
@@ -16,17 +19,18 @@ namespace vk {
 
 int32_t tree_level(vkzg_ctx* ctx, const Key& k, const uint32_t* d_row_ptr, uint64_t n_nodes, const uint16_t* d_slot,
                    const int32_t* d_child, const fp_t* d_lit, uint64_t n_terms, const affine_t* d_prev, affine_t* d_out, bool lit_raw);
+int32_t tree_ext_levels(vkzg_ctx* ctx, const Key& k, const fp_t* d_stem, const uint8_t* d_unit, const uint8_t* d_val, uint64_t n,
+                        uint32_t W, affine_t* d_all, uint64_t base0, uint64_t base1);
 
 struct HNode {
+    static constexpr uint32_t INLINE = 12;  // children kept inline before the node switches to a direct table
     bool internal = true;
-    bool clean = false;          // commit below is valid
-    affine_t commit;
-    // internal
-    std::vector<std::pair<uint8_t, uint32_t>> kids;  // (unit, node id), unsorted; direct table once it grows
-    std::vector<int32_t> table;                      // 256 entries or empty
-    // extension: the stem lives in the tree's byte arena (no per-node heap allocation), the first leaf inline
-    uint64_t stem_off = 0;
-    uint8_t leaf_unit = 0;
+    uint8_t nk = 0;              // inline children in use (internal nodes without a table)
+    uint8_t leaf_unit = 0;       // extension: the first leaf lives inline
+    int32_t table_id = -1;       // internal: index of this node's 256-entry direct table in the tree's table arena
+    uint8_t unit[INLINE];        // internal: (unit, node id) pairs in insertion order
+    uint32_t kid[INLINE];
+    uint64_t stem_off = 0;       // extension: the stem lives in the tree's byte arena (no per-node heap allocation)
     std::array<uint8_t, 32> leaf_val;
 };
 
@@ -36,34 +40,64 @@ struct vkzg_tree {
     uint32_t key_len = 0, ext_width = 0;
     std::vector<vk::HNode> nodes;  // node 0 is the root
     std::vector<uint8_t> stems;    // key bytes of every extension node
+    std::vector<int32_t> tables;   // 256 child ids (-1 = none) per internal node that outgrew its inline list
+    std::vector<vk::affine_t> commits;  // cached commitment per node id (valid where clean[id]); sized at commit time
+    std::vector<uint8_t> clean;    // per node id: the cached commitment is valid.  Kept out of the node records: the flags of a
+                                   // million nodes stay cache-resident for insertion (cleared along the path, node.rs:41,46,145,156)
+                                   // and for the sequential passes of vkzg_tree_commit
+    bool is_clean(uint32_t id) const { return id < clean.size() && clean[id]; }
+    uint64_t n_dirty = 1;          // nodes whose cached commitment is missing or cleared (the empty root to begin with)
     uint64_t n_keys = 0;
     uint64_t n_commits = 0;
     const uint8_t* stem(const vk::HNode& n) const { return stems.data() + n.stem_off; }
+    const int32_t* table(const vk::HNode& n) const { return tables.data() + (size_t)n.table_id * 256; }
 
     int32_t child(uint32_t id, uint8_t unit) const {
         const vk::HNode& n = nodes[id];
-        if (!n.table.empty()) return n.table[unit];
-        for (auto& kv : n.kids)
-            if (kv.first == unit) return (int32_t)kv.second;
+        if (n.table_id >= 0) return table(n)[unit];
+        for (uint32_t j = 0; j < n.nk; ++j)
+            if (n.unit[j] == unit) return (int32_t)n.kid[j];
         return -1;
     }
     void set_child(uint32_t id, uint8_t unit, uint32_t c) {
         vk::HNode& n = nodes[id];
-        bool found = false;
-        for (auto& kv : n.kids)
-            if (kv.first == unit) {
-                kv.second = c;
-                found = true;
-            }
-        if (!found) n.kids.push_back({unit, c});
-        if (!n.table.empty()) {
-            n.table[unit] = (int32_t)c;
-        } else if (n.kids.size() > 12) {
-            n.table.assign(256, -1);
-            for (auto& kv : n.kids) n.table[kv.first] = (int32_t)kv.second;
+        if (n.table_id >= 0) {
+            tables[(size_t)n.table_id * 256 + unit] = (int32_t)c;
+            return;
         }
+        for (uint32_t j = 0; j < n.nk; ++j)
+            if (n.unit[j] == unit) {
+                n.kid[j] = c;
+                return;
+            }
+        if (n.nk < vk::HNode::INLINE) {
+            n.unit[n.nk] = unit;
+            n.kid[n.nk] = c;
+            ++n.nk;
+            return;
+        }
+        n.table_id = (int32_t)(tables.size() / 256);
+        tables.resize(tables.size() + 256, -1);
+        int32_t* tb = tables.data() + (size_t)n.table_id * 256;
+        for (uint32_t j = 0; j < n.nk; ++j) tb[n.unit[j]] = (int32_t)n.kid[j];
+        tb[unit] = (int32_t)c;
+    }
+    // children in ascending unit order
+    template <typename F>
+    void for_each_child(const vk::HNode& n, F&& f) const {
+        if (n.table_id >= 0) {
+            const int32_t* tb = table(n);
+            for (uint32_t u = 0; u < 256; ++u)
+                if (tb[u] >= 0) f((uint8_t)u, (uint32_t)tb[u]);
+            return;
+        }
+        uint8_t order[vk::HNode::INLINE];
+        for (uint32_t j = 0; j < n.nk; ++j) order[j] = (uint8_t)j;
+        std::sort(order, order + n.nk, [&](uint8_t a, uint8_t b) { return n.unit[a] < n.unit[b]; });
+        for (uint32_t j = 0; j < n.nk; ++j) f(n.unit[order[j]], n.kid[order[j]]);
     }
     uint32_t new_ext(const uint8_t* key, const uint8_t* value) {
+        ++n_dirty;
         nodes.emplace_back();
         vk::HNode& e = nodes.back();
         e.internal = false;
@@ -77,7 +111,10 @@ struct vkzg_tree {
     bool insert(const uint8_t* key, const uint8_t* value) {
         uint32_t cur = 0, depth = 0;
         for (;;) {
-            nodes[cur].clean = false;  // cached commitments on the path are cleared
+            if (is_clean(cur)) {  // cached commitments on the path are cleared
+                clean[cur] = 0;
+                ++n_dirty;
+            }
             if (depth >= key_len) return false;
             uint8_t k = key[depth];
             int32_t c = child(cur, k);
@@ -93,7 +130,10 @@ struct vkzg_tree {
                 bool same = memcmp(est, key, key_len) == 0;
                 if (same || depth == key_len - 2) {
                     if (!same) return false;
-                    ext.clean = false;
+                    if (is_clean((uint32_t)c)) {
+                        clean[c] = 0;
+                        ++n_dirty;
+                    }
                     // same stem means same key, hence the same leaf unit: overwrite (node.rs:142-146)
                     memcpy(ext.leaf_val.data(), value, 32);
                     return true;
@@ -102,6 +142,7 @@ struct vkzg_tree {
                 while (d < key_len && est[d] == key[d]) ++d;
                 if (d >= key_len) return false;  // the stems only differ above this depth: the reference indexes out of bounds
                 uint8_t old_unit = est[d];
+                ++n_dirty;
                 nodes.emplace_back();
                 uint32_t inner = (uint32_t)nodes.size() - 1;
                 uint32_t e = new_ext(key, value);
@@ -113,6 +154,41 @@ struct vkzg_tree {
             }
             cur = (uint32_t)c;
             ++depth;
+        }
+    }
+    // Software prefetch for bulk insertion.  A walk along `key` is a chain of dependent reads: node header -> child slot
+    // (direct table entry; small nodes keep their children inline) -> next node header -> ... -> stem bytes.  prefetch_path performs the
+    // first `reads` of them on the CURRENT structure (read-only; the structure may still change before the key is
+    // inserted, a stale prefetch is harmless) and prefetches the target of the next one WITHOUT touching it.  The bulk
+    // loop calls it with increasing `reads` at decreasing look-ahead distances, so each call only dereferences lines
+    // an earlier call requested.
+    void prefetch_path(const uint8_t* key, uint32_t reads) const {
+        uint32_t cur = 0;
+        for (uint32_t depth = 0; depth < key_len; ++depth) {
+            const vk::HNode& n = nodes[cur];
+            if (reads-- == 0) {  // next read: this node's record (112 bytes: two or three lines)
+                __builtin_prefetch(&n);
+                __builtin_prefetch(reinterpret_cast<const char*>(&n) + 64);
+                __builtin_prefetch(reinterpret_cast<const char*>(&n) + sizeof(vk::HNode) - 1);
+                return;
+            }
+            if (!n.internal) {
+                __builtin_prefetch(stems.data() + n.stem_off);
+                return;
+            }
+            int32_t c = -1;
+            if (n.table_id >= 0) {
+                if (reads-- == 0) {  // next read: the child slot of the direct table
+                    __builtin_prefetch(table(n) + key[depth]);
+                    return;
+                }
+                c = table(n)[key[depth]];
+            } else {
+                for (uint32_t j = 0; j < n.nk; ++j)
+                    if (n.unit[j] == key[depth]) c = (int32_t)n.kid[j];
+            }
+            if (c < 0) return;
+            cur = (uint32_t)c;
         }
     }
     const uint8_t* get(const uint8_t* key) const {
@@ -151,6 +227,10 @@ struct LevelBuf {
         child.push_back(c);
         lit.push_back(l);
     }
+    void term_child(uint16_t s, int32_t c) {  // internal nodes: no literal travels
+        slot.push_back(s);
+        child.push_back(c);
+    }
     uint32_t close(uint32_t node) {
         row_ptr.push_back((uint32_t)slot.size());
         owner.push_back(node);
@@ -185,12 +265,26 @@ int32_t vkzg_tree_insert(vkzg_tree* t, const uint8_t* keys, const uint8_t* value
     if (!t || (n && (!keys || !values))) return VKZG_ERR_ARG;
     t->nodes.reserve(t->nodes.size() + n + n / 4 + 16);
     t->stems.reserve(t->stems.size() + n * t->key_len);
+    t->tables.reserve(t->tables.size() + 256 * (n / 13 + 16));
+    const uint64_t kl = t->key_len;
+    const bool timing = getenv("VKZG_TREE_TIMING") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
     for (uint64_t i = 0; i < n; ++i) {
+        // staged look-ahead: deeper levels of nearer keys (each stage reads only what an earlier stage prefetched)
+        // (root and the level-1 nodes stay cached: reads 0..3 are hits; 4 = level-2 header, 5 = its slot, 6 = the
+        // level-3 node (usually the extension), whose stem is the last line an insertion compares)
+        if (i + 16 < n) t->prefetch_path(keys + (i + 16) * kl, 4);
+        if (i + 12 < n) t->prefetch_path(keys + (i + 12) * kl, 5);
+        if (i + 8 < n) t->prefetch_path(keys + (i + 8) * kl, 6);
+        if (i + 4 < n) t->prefetch_path(keys + (i + 4) * kl, 7);
         if (!t->insert(keys + i * t->key_len, values + i * 32)) {
             if (n_done) *n_done = i;
             return VKZG_ERR_RANGE;
         }
     }
+    if (timing)
+        fprintf(stderr, "vkzg_tree_insert: %llu keys in %.1f ms\n", (unsigned long long)n,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     if (n_done) *n_done = n;
     return VKZG_OK;
 }
@@ -214,24 +308,41 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     if (!k || k->kind != VKZG_KEY_WINDOW || !t || !root_out) return VKZG_ERR_ARG;
     if (k->n < 256 || k->n < t->ext_width || k->n < 4) return VKZG_ERR_RANGE;
     if (n_committed) *n_committed = 0;
-    if (t->nodes[0].clean) {
-        memcpy(root_out, &t->nodes[0].commit, sizeof(affine_t));
+    if (t->is_clean(0)) {
+        memcpy(root_out, &t->commits[0], sizeof(affine_t));
         return VKZG_OK;
     }
+    t->commits.resize(t->nodes.size());
+    t->clean.resize(t->nodes.size(), 0);
+    const bool timing = getenv("VKZG_TREE_TIMING") != nullptr;  // phase times of this call on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_start = now();
     const uint32_t W = t->ext_width;
     // literals travel as raw little-endian integers when they fit 32 bytes (the device reduces and converts them);
     // longer stems are reduced on the host and everything travels in Montgomery form
     const bool raw = t->key_len <= 32;
-    auto literal = [raw](const uint8_t* b, size_t len) {
-        if (!raw) return fr_from_le_bytes(b, len);
-        fp_t v = fp_zero<S>();
-        memcpy(v.l, b, len);
-        return v;
-    };
+    auto literal = [](const uint8_t* b, size_t len) { return fr_from_le_bytes(b, len); };
     // ---- post-order over the dirty part: heights -> levels.  Level 0 = C1 / C2 helper vectors, 1 = extensions,
     //      >= 2 internal nodes by height.  Clean children enter as known commitments (prefix of the node array).
+    // Short keys (raw): the dirty extensions travel in compact form (stem, leaf unit, value: 65 bytes each) and the device
+    // writes the CSR rows of levels 0 and 1 itself (k_tree_ext_expand); levels[0] / levels[1] then only carry the owners.
+    // The records are written straight into the context's pinned staging area: [stems | values | units], capacity = the
+    // number of dirty nodes (an upper bound on the dirty extensions).
+    const size_t ext_cap = raw ? (size_t)std::min<uint64_t>(t->n_dirty, t->nodes.size()) : 0;
+    uint8_t* stage = nullptr;
+    if (ext_cap) {
+        stage = (uint8_t*)ctx->pinned_stage(0, ext_cap * 65);
+        if (!stage) return VKZG_ERR_OOM;
+    }
+    fp_t* ext_stem = (fp_t*)stage;
+    uint8_t* ext_val = stage + ext_cap * 32;
+    uint8_t* ext_unit = stage + ext_cap * 64;
+    size_t n_ext = 0;
     std::vector<LevelBuf> levels(2);
-    if (t->n_commits == 0) {  // first (bulk) commit: every node is dirty, size the leaf-side levels once
+    if (raw) {
+        levels[0].owner.reserve(ext_cap);
+        levels[1].owner.reserve(ext_cap);
+    } else if (t->n_commits == 0) {  // first (bulk) commit: every node is dirty, size the leaf-side levels once
         const size_t nn = t->nodes.size();
         levels[0].slot.reserve(2 * nn); levels[0].child.reserve(2 * nn); levels[0].lit.reserve(2 * nn);
         levels[0].row_ptr.reserve(nn + 1); levels[0].owner.reserve(nn);
@@ -242,18 +353,47 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     std::vector<affine_t> known;            // commitments of clean children referenced by dirty parents
     std::vector<std::pair<uint32_t, int32_t>> handle(t->nodes.size(), {0xffffffffu, -1});  // node -> (level, row) ; level 0xfffffffe = known
     std::vector<std::pair<uint32_t, bool>> stack{{0u, false}};
-    fp_t one = fp_one<S>(), zero = fp_zero<S>();
-    if (raw) {
-        one = zero;
-        one.l[0] = 1;
+    const fp_t one = fp_one<S>(), zero = fp_zero<S>();
+    bool overflow = false;
+    auto push_ext_compact = [&](uint32_t id, const HNode& n) {
+        if (n_ext >= ext_cap) {  // cannot happen while n_dirty is maintained; never write past the staging area
+            overflow = true;
+            return;
+        }
+        fp_t st = fp_zero<S>();
+        memcpy(st.l, t->stem(n), t->key_len);
+        ext_stem[n_ext] = st;
+        memcpy(ext_val + n_ext * 32, n.leaf_val.data(), 32);
+        ext_unit[n_ext] = n.leaf_unit;
+        ++n_ext;
+        levels[0].owner.push_back(0xffffffffu);
+        levels[1].owner.push_back(id);
+        handle[id] = {1u, (int32_t)levels[1].owner.size() - 1};
+    };
+    // Bulk mode (a large part of the tree is dirty, e.g. the first commit after loading): ONE sequential pass over the node
+    // array emits the dirty extensions in id order, so the depth-first walk below only visits the (few) internal nodes
+    // and never touches an extension's memory.  With few dirty nodes the walk alone does
+    // everything and the cost stays proportional to the dirty paths.
+    const bool bulk = raw && (ctx->tree_flatten == 1 || (ctx->tree_flatten == 0 && t->n_dirty * 8 > t->nodes.size()));
+    if (bulk) {
+        const size_t nn = t->nodes.size();
+        for (size_t id = 0; id < nn; ++id) {
+            if (t->clean[id]) continue;  // a clean node's record is not even read
+            const HNode& n = t->nodes[id];
+            if (!n.internal) push_ext_compact((uint32_t)id, n);
+        }
     }
     while (!stack.empty()) {
         auto [id, done] = stack.back();
         stack.pop_back();
-        HNode& n = t->nodes[id];
-        if (n.clean) {
-            known.push_back(n.commit);
+        if (t->clean[id]) {
+            known.push_back(t->commits[id]);
             handle[id] = {0xfffffffeu, (int32_t)known.size() - 1};
+            continue;
+        }
+        HNode& n = t->nodes[id];
+        if (!n.internal && raw) {
+            if (!bulk) push_ext_compact(id, n);
             continue;
         }
         if (!n.internal) {
@@ -279,25 +419,34 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
             handle[id] = {1u, (int32_t)levels[1].close(id)};
             continue;
         }
+        // one scan of the children; a second visit (after the children are placed) only if some child still has to be
+        // walked — nodes whose children are all extensions or cached are finished on the first visit
+        uint32_t level = 2, nc = 0, pending = 0;
+        uint8_t cu[256];
+        uint32_t cc[256];
+        t->for_each_child(n, [&](uint8_t u, uint32_t c) {
+            cu[nc] = u;
+            cc[nc++] = c;
+        });
         if (!done) {
-            stack.push_back({id, true});
-            for (auto& kv : n.kids) stack.push_back({kv.second, false});
-            continue;
+            for (uint32_t j = 0; j < nc; ++j)
+                if (handle[cc[j]].first == 0xffffffffu) {  // not placed yet (bulk: the dirty extensions already have their row)
+                    if (!pending++) stack.push_back({id, true});
+                    stack.push_back({cc[j], false});
+                }
+            if (pending) continue;
         }
-        uint32_t level = 2;
-        for (auto& kv : n.kids) {
-            auto h = handle[kv.second];
+        for (uint32_t j = 0; j < nc; ++j) {
+            auto h = handle[cc[j]];
             if (h.first != 0xfffffffeu) level = std::max(level, h.first + 1);
         }
         if (levels.size() <= level) levels.resize(level + 1);
-        std::vector<std::pair<uint8_t, uint32_t>> kids = n.kids;
-        std::sort(kids.begin(), kids.end());
-        for (auto& kv : kids) {
-            // child reference encoded as (level << 40 | row) is too wide for int32: store node id, resolve below
-            levels[level].term(kv.first, (int32_t)kv.second, zero);
-        }
+        // child reference encoded as (level << 40 | row) is too wide for int32: store node id, resolve below
+        for (uint32_t j = 0; j < nc; ++j) levels[level].term_child(cu[j], (int32_t)cc[j]);
         handle[id] = {level, (int32_t)levels[level].close(id)};
     }
+    if (overflow) return VKZG_ERR_RANGE;
+    auto t_flat = now();
     // ---- internal levels: order the nodes of a level by their number of children, so that the lanes / groups of one
     //      warp (one node each) walk term lists of similar length instead of waiting for the longest
     for (size_t l = 2; l < levels.size(); ++l) {
@@ -312,10 +461,9 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         LevelBuf S;
         S.slot.reserve(L.slot.size());
         S.child.reserve(L.child.size());
-        S.lit.reserve(L.lit.size());
         for (size_t j = 0; j < nn; ++j) {
             uint32_t r = perm[j];
-            for (uint32_t t2 = L.row_ptr[r]; t2 < L.row_ptr[r + 1]; ++t2) S.term(L.slot[t2], L.child[t2], L.lit[t2]);
+            for (uint32_t t2 = L.row_ptr[r]; t2 < L.row_ptr[r + 1]; ++t2) S.term_child(L.slot[t2], L.child[t2]);
             uint32_t row = S.close(L.owner[r]);
             handle[L.owner[r]] = {(uint32_t)l, (int32_t)row};
         }
@@ -336,11 +484,21 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
             auto h = handle[(uint32_t)c];
             c = h.first == 0xfffffffeu ? h.second : (int32_t)(base[h.first] + (uint64_t)h.second);
         }
+    auto t_ids = now();
     // ---- device passes
     DevBuf<affine_t> all;
     VK_TRY(all.alloc(ctx, total));
     if (!known.empty()) VK_CUDA(cudaMemcpyAsync(all.p, known.data(), known.size() * sizeof(affine_t), cudaMemcpyHostToDevice, ctx->stream));
-    for (size_t l = 0; l < levels.size(); ++l) {
+    if (n_ext) {
+        DevBuf<fp_t> d_st;
+        DevBuf<uint8_t> d_un, d_va;
+        VK_TRY(upload(ctx, d_st, ext_stem, n_ext));
+        VK_TRY(upload(ctx, d_un, ext_unit, n_ext));
+        VK_TRY(upload(ctx, d_va, ext_val, n_ext * 32));
+        VK_TRY(tree_ext_levels(ctx, *k, d_st, d_un, d_va, n_ext, W, all.p, base[0], base[1]));
+        VK_TRY(stream_sync(ctx));
+    }
+    for (size_t l = raw ? 2 : 0; l < levels.size(); ++l) {
         LevelBuf& L = levels[l];
         uint64_t nn = L.owner.size();
         if (!nn) continue;
@@ -351,27 +509,37 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         VK_TRY(upload(ctx, d_rp, L.row_ptr.data(), nn + 1));
         VK_TRY(upload(ctx, d_sl, L.slot.data(), L.slot.size()));
         VK_TRY(upload(ctx, d_ch, L.child.data(), L.child.size()));
-        VK_TRY(upload(ctx, d_li, L.lit.data(), L.lit.size()));
+        if (!L.lit.empty()) VK_TRY(upload(ctx, d_li, L.lit.data(), L.lit.size()));  // internal levels carry no literals
         VK_TRY(tree_level(ctx, *k, d_rp, nn, d_sl, d_ch, d_li, L.slot.size(), all.p, all.p + base[l], raw));
         VK_TRY(stream_sync(ctx));  // the host vectors of this level go out of use before the next upload reuses the pool
     }
+    auto t_dev = now();
     // ---- cache the new commitments on the host
-    std::vector<affine_t> host(total - known.size());
-    if (!host.empty()) VK_CUDA(cudaMemcpyAsync(host.data(), all.p + known.size(), host.size() * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // (the level-0 helper rows C1 / C2 belong to no node and stay on the device)
+    const size_t n_new = total - base[1];
+    const affine_t* host = (const affine_t*)ctx->pinned_stage(1, n_new * sizeof(affine_t));
+    if (!host) return VKZG_ERR_OOM;
+    VK_CUDA(cudaMemcpyAsync((void*)host, all.p + base[1], n_new * sizeof(affine_t), cudaMemcpyDeviceToHost, ctx->stream));
     VK_TRY(stream_sync(ctx));
     uint64_t off = 0;
-    for (size_t l = 0; l < levels.size(); ++l) {
+    for (size_t l = 1; l < levels.size(); ++l) {
         for (size_t j = 0; j < levels[l].owner.size(); ++j) {
             uint32_t id = levels[l].owner[j];
             if (id != 0xffffffffu) {
-                t->nodes[id].commit = host[off + j];
-                t->nodes[id].clean = true;
+                t->commits[id] = host[off + j];
+                t->clean[id] = 1;
             }
         }
         off += levels[l].owner.size();
     }
-    if (n_committed) *n_committed = host.size();
-    memcpy(root_out, &t->nodes[0].commit, sizeof(affine_t));
+    if (timing) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "vkzg_tree_commit: %zu rows; flatten %.1f ms, sort+ids %.1f ms, upload+kernels %.1f ms, cache-back %.1f ms\n",
+                n_new, ms(t_start, t_flat), ms(t_flat, t_ids), ms(t_ids, t_dev), ms(t_dev, now()));
+    }
+    t->n_dirty = 0;
+    if (n_committed) *n_committed = n_new;
+    memcpy(root_out, &t->commits[0], sizeof(affine_t));
     return VKZG_OK;
 }
 

@@ -72,6 +72,25 @@ struct vkzg_ctx {
     cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
     cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
     bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
+    int tree_flatten = 0;                // VKZG_OPT_TREE_FLATTEN
+    // grow-only pinned host staging areas (vkzg_tree_commit: compact node records up, commitments down); pages stay
+    // resident and DMA-able between calls instead of being faulted in and staged by the driver every time
+    void* host_stage[2] = {nullptr, nullptr};
+    size_t host_stage_bytes[2] = {0, 0};
+    void* pinned_stage(int slot, size_t bytes) {
+        if (bytes > host_stage_bytes[slot]) {
+            if (host_stage[slot]) cudaFreeHost(host_stage[slot]);
+            host_stage[slot] = nullptr;
+            host_stage_bytes[slot] = 0;
+            size_t want = bytes + bytes / 4;
+            if (cudaMallocHost(&host_stage[slot], want) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            host_stage_bytes[slot] = want;
+        }
+        return host_stage[slot];
+    }
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     uint64_t timing_units = 0;  // point additions issued by the timed launches (upper bound: zero digits excluded at run time)

@@ -63,6 +63,9 @@ class Engine:
     def launches(self):
         return int(self._L.vkzg_ctx_launches(self._ctx))
 
+    OPT_IPA_TWO_STREAMS = 1   # include/vkzg.h
+    OPT_TREE_FLATTEN = 2      # 0 automatic, 1 bulk pass, 2 depth-first walk of the dirty paths
+
     def set_option(self, option, value):
         check(self._L.vkzg_ctx_set_option(self._ctx, ctypes.c_int32(option), ctypes.c_int32(value)), "vkzg_ctx_set_option")
 
