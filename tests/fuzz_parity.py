@@ -17,6 +17,9 @@ def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     eng = Engine(0)
     rng = np.random.default_rng(int(time.time()))
+    tk0, tk1 = orc.rand_fr(rng, 2)
+    tree_bases = orc.points_walk(tk0, tk1, 256)
+    tree_key = eng.load_key(tree_bases, window_bits=8)
     t0 = time.time()
     it = 0
     while time.time() - t0 < budget:
@@ -48,7 +51,60 @@ def main():
             eL, eR, etip, ey = orc.ipa_prove(bases, N, a[i], C[i], zb[i])
             assert (L[i] == eL).all() and (R[i] == eR).all() and (tip[i] == etip).all() and (y[i] == ey).all(), ("ipa", N, c, zs[i])
         assert eng.ipa_verify_batch(key, zb, C, L, R, tip, y).all()
+        # multiproof over m queries of this key (IPA scheme; multiproof.rs:99-176), random group skew
+        if N >= 4:
+            m = int(rng.integers(1, 50))
+            f = orc.rand_fr_buf(rng, m * N).reshape(m, N, 32)
+            Cm = eng.commit_batch(key, f)
+            z = rng.integers(0, N if rng.random() < 0.5 else 2, m).astype(np.uint64)
+            ym = np.stack([f[i, int(z[i])] for i in range(m)])
+            got = eng.multiproof_prove(key, "ipa", f, Cm, z, ym)
+            exp = orc.multiproof_prove("ipa", bases, N, f, Cm, z, ym)
+            assert all((got[k] == exp[k]).all() for k in ("D", "L", "R", "tip", "y")), ("multiproof", N, c, m)
+            assert eng.multiproof_verify_ipa(key, Cm, z, ym, got)
         key.free()
+        # KZG open over a Lagrange SRS (kzg/mod.rs:136-154): in-domain indices and outside points
+        srs = orc.kzg_setup(N, 100)
+        kk = eng.load_key(srs, window_bits=c)
+        Bk = int(rng.integers(1, 8))
+        fk = orc.rand_fr_buf(rng, Bk * N).reshape(Bk, N, 32)
+        zk = [int(rng.integers(0, N)) if rng.random() < 0.5 else int(rng.integers(N + 1, 1 << 40)) for _ in range(Bk)]
+        zkb = orc.fr_to_buf(zk)
+        pf, yk = eng.kzg_open_batch(kk, fk, zkb)
+        for i in range(Bk):
+            epf, ey, ok = orc.kzg_prove(srs, fk[i], zkb[i])
+            assert ok and (pf[i] == epf).all() and (yk[i] == ey).all(), ("kzg", N, c, zk[i])
+        kk.free()
+        # native host tree against the oracle's replay of the same insertion sequence, random flatten mode
+        if tree_key is not None and it % 4 == 0:
+            from verkle_kzg_b200.tree import NativeVerkleTree, VerkleTree
+            kl = int(rng.choice([3, 4, 8, 32, 40]))
+            width = int(rng.choice([1, 2, 3, 32, 256]))
+            nk = int(rng.integers(1, 400))
+            keys = rng.integers(0, int(rng.choice([3, 256])), (nk, kl), dtype=np.uint8)
+            _, first = np.unique(keys[:, : kl - 1], axis=0, return_index=True)
+            keys = keys[np.sort(first)]
+            vals = rng.integers(0, 256, (len(keys), 32), dtype=np.uint8)
+            ref = VerkleTree(kl, 256)
+            keep = 0
+            for k_, v_ in zip(keys, vals):
+                try:
+                    ref.insert_single(k_, v_)
+                    keep += 1
+                except ValueError:
+                    break
+            keys, vals = keys[:keep], vals[:keep]
+            if keep:
+                eng.set_option(eng.OPT_TREE_FLATTEN, int(rng.integers(0, 3)))
+                nt = NativeVerkleTree(kl, ext_width=width)
+                cut = int(rng.integers(0, keep + 1))
+                nt.insert_many(keys[:cut], vals[:cut])
+                if cut:
+                    assert (nt.commitment(eng, tree_key) == orc.tree_commit(tree_bases, keys[:cut], vals[:cut], ext_width=width)).all(), ("tree-a", kl, width)
+                nt.insert_many(keys[cut:], vals[cut:])
+                assert (nt.commitment(eng, tree_key) == orc.tree_commit(tree_bases, keys, vals, ext_width=width)).all(), ("tree-b", kl, width, cut)
+                nt.close()
+                eng.set_option(eng.OPT_TREE_FLATTEN, 0)
         # MSM
         n = int(rng.integers(1, 3000))
         cm = int(rng.choice([6, 9, 12, 16]))
