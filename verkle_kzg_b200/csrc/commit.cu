@@ -9,6 +9,7 @@
 // gather per addition (the next entry's point is in flight while the current one is added).  The 32
 // accumulators are summed with a shuffle tree.
 #include "vk_common.cuh"
+#include "warp_util.cuh"
 
 namespace vk {
 
@@ -46,18 +47,6 @@ __device__ __forceinline__ void emit_entries(const fp_t& k, uint32_t row_base /*
             list[pos] = (((row_base + w) << (c - 1)) + (mag - 1)) | (neg << 31);
         }
     }
-}
-
-__device__ __forceinline__ xyzz_t shfl_xor_xyzz_c(const xyzz_t& v, int mask) {
-    xyzz_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        r.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], mask);
-        r.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], mask);
-        r.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], mask);
-        r.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], mask);
-    }
-    return r;
 }
 
 // LPJ lanes per job (32, 16, 8, 4, 2 or 1): a warp runs 32 / LPJ jobs side by side, each group of LPJ lanes with its own
@@ -154,10 +143,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
     }
     xyzz_canon(acc);
 #pragma unroll 1
-    for (int off = LPJ / 2; off > 0; off >>= 1) {
-        xyzz_t o = shfl_xor_xyzz_c(acc, off);
-        acc = xyzz_add_ni(acc, o);
-    }
+    for (int off = LPJ / 2; off > 0; off >>= 1) acc = xyzz_add_pair(acc, off);
     if (gl == 0 && live) {
         fp_store(&out[vjob].x, acc.x);
         fp_store(&out[vjob].y, acc.y);
@@ -173,11 +159,10 @@ __global__ void __launch_bounds__(128) k_sum_slices(const xyzz_t* __restrict__ p
     if (job >= jobs) return;
     xyzz_t acc = xyzz_inf();
     for (uint32_t s = lane; s < split; s += 32) acc = xyzz_add_ni(acc, part[job * split + s]);
+    int top = 16;  // only as many levels as there are slices
+    while (top > 1 && (uint32_t)top >= split) top >>= 1;
 #pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-        xyzz_t o = shfl_xor_xyzz_c(acc, off);
-        acc = xyzz_add_ni(acc, o);
-    }
+    for (int off = top; off > 0; off >>= 1) acc = xyzz_add_pair(acc, off);
     if (lane == 0) out[job] = acc;
 }
 
@@ -238,10 +223,12 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
     }
     // few wide dense jobs (single proofs / commits): slice every job over several warps so the whole GPU works on it
     if (!d_row_ptr && T >= 16 && jobs * 8 <= (uint64_t)ctx->sm_count * 16) {
-        uint32_t split = (T + 7) / 8;  // ~8 terms (128 table additions) per warp
+        // latency-bound: ~4 terms (2-4 additions per lane) per warp, at most 32 slices so that k_sum_slices is one shuffle
+        // tree — every halving of the per-lane chain costs one more 7-product fold level, which is where it stops paying
+        uint32_t split = (T + 3) / 4;
         uint64_t room = (uint64_t)ctx->sm_count * 16 / jobs;
         if (split > room) split = (uint32_t)room;
-        if (split > 64) split = 64;
+        if (split > 32) split = 32;
         if (split > 1) {
             DevBuf<xyzz_t> part;
             VK_TRY(part.alloc(ctx, jobs * split));

@@ -156,23 +156,29 @@ __global__ void __launch_bounds__(64) k_ipa_transcript_begin(IpaState st, uint64
 // fold by the previous round's challenge (ipa/mod.rs:308-310), then the scalars of round `round`.
 //   fold_m  = half length of the round just finished (0: nothing to fold)
 //   m       = half length of this round (0: no scalars, final call -> tip)
-__global__ void __launch_bounds__(128) k_ipa_fold_scalars(IpaState st, uint64_t B, uint32_t N, uint32_t fold_m, uint32_t m,
-                                                          uint32_t T, bool with_b, fp_t* __restrict__ tip_out) {
-    uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (p >= B) return;
+// G threads per proof: 32 (a warp; big batches) or 256 (a whole CTA; a handful of proofs, where the kernel is a chain of
+// dependent products per thread and eight times more threads make it eight times shorter).
+template <int G>
+__global__ void __launch_bounds__(G == 32 ? 128 : G) k_ipa_fold_scalars(IpaState st, uint64_t B, uint32_t N, uint32_t fold_m, uint32_t m,
+                                                                        uint32_t T, bool with_b, fp_t* __restrict__ tip_out) {
+    uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    uint32_t lane = threadIdx.x % G;
+    if (p >= B) return;  // (G == 256: the whole CTA leaves together)
     fp_t* a = st.a + p * N;
     fp_t* b = st.b + p * N;
     fp_t* coef = st.coef + p * N;
     if (fold_m) {
         fp_t x = fp_load(st.x + p);
-        for (uint32_t j = lane; j < fold_m; j += 32) {
+        for (uint32_t j = lane; j < fold_m; j += G) {
             fp_store(a + j, fp_add<S>(fp_load(a + j), fp_mul<S>(x, fp_load(a + fold_m + j))));
             if (with_b) fp_store(b + j, fp_add<S>(fp_load(b + fold_m + j), fp_mul<S>(x, fp_load(b + j))));
         }
-        for (uint32_t i = lane; i < N; i += 32)
+        for (uint32_t i = lane; i < N; i += G)
             if ((i & (2 * fold_m - 1)) < fold_m) fp_store(coef + i, fp_mul<S>(fp_load(coef + i), x));
-        __syncwarp();
+        if (G == 32)
+            __syncwarp();
+        else
+            __syncthreads();
     }
     if (m == 0) {
         if (lane == 0) fp_store(tip_out + p, fp_load(a));
@@ -181,25 +187,47 @@ __global__ void __launch_bounds__(128) k_ipa_fold_scalars(IpaState st, uint64_t 
     fp_t* scL = st.sc + (2 * p) * T;
     fp_t* scR = scL + T;
     const uint32_t half = N / 2;
-    for (uint32_t j = lane; j < half; j += 32) {
+    for (uint32_t j = lane; j < half; j += G) {
         uint32_t blk = (j / m) * 2 * m, r = j % m;
         fp_store(scL + j, fp_mul<S>(fp_load(coef + blk + m + r), fp_load(a + r)));
         fp_store(scR + j, fp_mul<S>(fp_load(coef + blk + r), fp_load(a + m + r)));
     }
     if (with_b) {
         fp_t ipl = fp_zero<S>(), ipr = fp_zero<S>();
-        for (uint32_t j = lane; j < m; j += 32) {
+        for (uint32_t j = lane; j < m; j += G) {
             ipl = fp_add<S>(ipl, fp_mul<S>(fp_load(a + j), fp_load(b + m + j)));
             ipr = fp_add<S>(ipr, fp_mul<S>(fp_load(a + m + j), fp_load(b + j)));
         }
         ipl = warp_sum_fr(ipl);
         ipr = warp_sum_fr(ipr);
+        if (G > 32) {  // across the warps of the CTA
+            __shared__ fp_t red[2][G / 32];
+            if ((lane & 31) == 0) {
+                red[0][lane >> 5] = ipl;
+                red[1][lane >> 5] = ipr;
+            }
+            __syncthreads();
+            if (lane == 0)
+                for (int k = 1; k < G / 32; ++k) {
+                    ipl = fp_add<S>(ipl, red[0][k]);
+                    ipr = fp_add<S>(ipr, red[1][k]);
+                }
+        }
         if (lane == 0) {
             fp_t w = fp_load(st.w + p);
             fp_store(scL + half, fp_mul<S>(w, ipl));
             fp_store(scR + half, fp_mul<S>(w, ipr));
         }
     }
+}
+
+static int32_t launch_fold_scalars(vkzg_ctx* ctx, IpaState st, uint64_t B, uint32_t N, uint32_t fold_m, uint32_t m, uint32_t T,
+                                   bool with_b, fp_t* tip_out) {
+    if (B <= 64 && N >= 64)  // latency-bound: a CTA per proof
+        k_ipa_fold_scalars<256><<<(uint32_t)B, 256, 0, ctx->stream>>>(st, B, N, fold_m, m, T, with_b, tip_out);
+    else
+        k_ipa_fold_scalars<32><<<ceil_div_u64(B * 32, 128), 128, 0, ctx->stream>>>(st, B, N, fold_m, m, T, with_b, tip_out);
+    return launch_check(ctx);
 }
 
 // L, R -> affine (one inversion), outputs, transcript, challenge (ipa/mod.rs:301-306)
@@ -310,14 +338,12 @@ static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint3
     VK_TRY(launch_check(ctx));
     for (uint32_t r = 0; r < rounds; ++r) {
         uint32_t m = N >> (r + 1);
-        k_ipa_fold_scalars<<<wblocks, 128, 0, s>>>(st, B, N, r ? 2 * m : 0, m, T, with_b, nullptr);
-        VK_TRY(launch_check(ctx));
+        VK_TRY(launch_fold_scalars(ctx, st, B, N, r ? 2 * m : 0, m, T, with_b, nullptr));
         VK_TRY(fixed_base_msm(ctx, k, sc, T, 2 * B, m, with_b ? k.n : 0xffffffffu, lr));
         k_ipa_challenge<<<ceil_div_u64(B, 64), 64, 0, s>>>(st, B, r, rounds, d_L, d_R);
         VK_TRY(launch_check(ctx));
     }
-    k_ipa_fold_scalars<<<wblocks, 128, 0, s>>>(st, B, N, 1, 0, T, with_b, d_tip);
-    return launch_check(ctx);
+    return launch_fold_scalars(ctx, st, B, N, 1, 0, T, with_b, d_tip);
 }
 
 

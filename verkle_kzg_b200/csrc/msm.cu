@@ -15,6 +15,7 @@
 // The order in which a bucket's points are added is not deterministic (atomics), the result is: it leaves
 // the device in canonical affine form.
 #include "vk_common.cuh"
+#include "warp_util.cuh"
 
 namespace vk {
 
@@ -99,18 +100,6 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ counts, ui
     if (threadIdx.x == 1023) offsets[n] = sh[1023];
 }
 
-__device__ __forceinline__ xyzz_t shfl_xor_xyzz(const xyzz_t& v, int mask) {
-    xyzz_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        r.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], mask);
-        r.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], mask);
-        r.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], mask);
-        r.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], mask);
-    }
-    return r;
-}
-
 // P (power of two <= 32) adjacent lanes per bucket
 __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                     const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P, uint32_t cap,
@@ -150,10 +139,7 @@ __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restric
     }
     xyzz_canon(acc);
 #pragma unroll 1
-    for (uint32_t m = 1; m < P; m <<= 1) {
-        xyzz_t o = shfl_xor_xyzz(acc, (int)m);
-        acc = xyzz_add_ni(acc, o);
-    }
+    for (uint32_t m = 1; m < P; m <<= 1) acc = xyzz_add_pair(acc, (int)m);
     if (live && p == 0) {
         fp_store(&buckets[b].x, acc.x);
         fp_store(&buckets[b].y, acc.y);

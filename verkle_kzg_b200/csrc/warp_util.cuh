@@ -56,4 +56,62 @@ static __device__ __noinline__ fp_t warp_inverse_of_lane_products_t(const fp_t t
 }
 static __device__ __forceinline__ fp_t warp_inverse_of_lane_products(const fp_t t) { return warp_inverse_of_lane_products_t<S>(t); }
 
+__device__ __forceinline__ xyzz_t shfl_xor_point(const xyzz_t& v, int mask) {
+    xyzz_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_xor_sync(0xffffffffu, v.x.l[i], mask);
+        r.y.l[i] = __shfl_xor_sync(0xffffffffu, v.y.l[i], mask);
+        r.zz.l[i] = __shfl_xor_sync(0xffffffffu, v.zz.l[i], mask);
+        r.zzz.l[i] = __shfl_xor_sync(0xffffffffu, v.zzz.l[i], mask);
+    }
+    return r;
+}
+__device__ __forceinline__ fp_t fp_sel(bool c, const fp_t& a, const fp_t& b) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+
+// One level of a shuffle-tree fold: returns mine + (the accumulator of lane ^ off) on BOTH lanes of the pair.
+// xyzz_add costs 14 products; the two lanes of a pair would compute the same 14 redundantly, so they split them
+// instead — 2 + 3 + 2 products per lane with the intermediate values exchanged by shuffles — which halves the
+// dependent multiplier chain of a fold level (what a latency-bound single proof waits for) and the redundant pipe
+// work of the big batches.  Inputs canonical; all 32 lanes must call it (full-mask shuffles; the special cases —
+// an identity operand, equal or opposite points — are resolved after the last shuffle).
+static __device__ __noinline__ xyzz_t xyzz_add_pair(const xyzz_t mine, int off) {
+    const bool A = ((threadIdx.x & 31) & off) == 0;  // lane A holds operand a, lane B operand b; result = a + b
+    const xyzz_t other = shfl_xor_point(mine, off);
+    // U1 = a.x b.zz, S1 = a.y b.zzz on A;  U2 = b.x a.zz, S2 = b.y a.zzz on B
+    fp_t t1 = fp_mul_ni<Q>(mine.x, other.zz), t2 = fp_mul_ni<Q>(mine.y, other.zzz);
+    fp_t o1 = shfl_xor_fpw(t1, off), o2 = shfl_xor_fpw(t2, off);
+    const fp_t U1 = fp_sel(A, t1, o1), U2 = fp_sel(A, o1, t1), S1 = fp_sel(A, t2, o2), S2 = fp_sel(A, o2, t2);
+    const fp_t P = fp_sub<Q>(U2, U1), R = fp_sub<Q>(S2, S1);
+    // A: PP = P^2, PPP = P PP, Q = U1 PP;   B: RR = R^2, ZZ12 = a.zz b.zz, ZZZ12 = a.zzz b.zzz
+    const fp_t sq = fp_sel(A, P, R);
+    fp_t v1 = fp_mul_ni<Q>(sq, sq);
+    fp_t v2 = fp_mul_ni<Q>(fp_sel(A, P, mine.zz), fp_sel(A, v1, other.zz));
+    fp_t v3 = fp_mul_ni<Q>(fp_sel(A, U1, mine.zzz), fp_sel(A, v1, other.zzz));
+    o1 = shfl_xor_fpw(v1, off);
+    o2 = shfl_xor_fpw(v2, off);
+    fp_t o3 = shfl_xor_fpw(v3, off);
+    const fp_t PP = fp_sel(A, v1, o1), RR = fp_sel(A, o1, v1), PPP = fp_sel(A, v2, o2), ZZ12 = fp_sel(A, o2, v2);
+    const fp_t Qv = fp_sel(A, v3, o3), ZZZ12 = fp_sel(A, o3, v3);
+    xyzz_t r;
+    r.x = fp_sub<Q>(fp_sub<Q>(RR, PPP), fp_dbl<Q>(Qv));
+    // A: Y3 = R (Q - X3) - S1 PPP;   B: ZZ3 = ZZ12 PP, ZZZ3 = ZZZ12 PPP
+    fp_t w1 = fp_mul_ni<Q>(fp_sel(A, R, ZZ12), fp_sel(A, fp_sub<Q>(Qv, r.x), PP));
+    fp_t w2 = fp_mul_ni<Q>(fp_sel(A, S1, ZZZ12), PPP);
+    o1 = shfl_xor_fpw(w1, off);
+    o2 = shfl_xor_fpw(w2, off);
+    r.y = fp_sub<Q>(fp_sel(A, w1, o1), fp_sel(A, w2, o2));
+    r.zz = fp_sel(A, o1, w1);
+    r.zzz = fp_sel(A, o2, w2);
+    if (xyzz_is_inf(mine)) return other;
+    if (xyzz_is_inf(other)) return mine;
+    if (fp_is_zero(P)) return A ? xyzz_add_ni(mine, other) : xyzz_add_ni(other, mine);  // doubling / opposite points
+    return r;
+}
+
 }  // namespace vk
