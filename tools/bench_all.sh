@@ -1,7 +1,7 @@
 #!/bin/bash
 # every workload once (1 GPU); JSON lines go to gpurun_out/bench_all_r1.jsonl
 out=gpurun_out/bench_all_r1.jsonl; : > $out
-for w in ipa commit kzg multiproof; do python bench.py --workload $w --steps 5 --warmup 3 2>gpurun_out/ba_$w.err >> $out || tail -3 gpurun_out/ba_$w.err; done
+for w in ipa commit kzg multiproof tree; do python bench.py --workload $w --steps 5 --warmup 3 2>gpurun_out/ba_$w.err >> $out || tail -3 gpurun_out/ba_$w.err; done
 for l in 16 18 20; do python bench.py --workload msm --log2n $l --steps 5 --warmup 3 2>gpurun_out/ba_msm$l.err >> $out || tail -3 gpurun_out/ba_msm$l.err; done
 python - <<'PY'
 import json
