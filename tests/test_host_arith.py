@@ -45,6 +45,10 @@ def test_field_ops(hc, tag, mod):
     assert dec(_op(hc, tag, 2, a, b)) == [(x * y) % mod for x, y in zip(xs, ys)]
     assert dec(_op(hc, tag, 6, a)) == [(-x) % mod for x in xs]
     nz = [x for x in xs[:400] + edge + [3, 5, (mod - 1) // 3, 1 << 200, (1 << 253) + 12345] if x]
+    # Montgomery representatives with long runs of trailing zeros (the binary inversion strips them up to 31 at a time)
+    rinv0 = pow(orc.MONT_R, -1, mod)
+    nz += [((1 << j) * rinv0) % mod for j in (1, 31, 32, 33, 63, 64, 95, 96, 200, 253)]
+    nz += [(((1 << j) * 0xdeadbeef1) * rinv0) % mod for j in (31, 32, 64, 128)]
     assert dec(_op(hc, tag, 3, enc(nz))) == [pow(x, -1, mod) for x in nz]
     assert dec(_op(hc, tag, 7, enc(nz))) == [pow(x, -1, mod) for x in nz]
     assert dec(_op(hc, tag, 3, enc([0]))) == [0]

@@ -514,6 +514,24 @@ VK_HD void shl1_8(uint32_t* x) {
     x[0] <<= 1;
 }
 
+// x is even and non-zero: x >>= z, y <<= z, k += z for z = the number of trailing zero bits of x (31 at a time)
+VK_HD void strip_zeros8(uint32_t* x, uint32_t* y, uint32_t& k) {
+    while ((x[0] & 1) == 0) {
+#ifdef __CUDA_ARCH__
+        const uint32_t z = x[0] ? (uint32_t)__ffs((int)x[0]) - 1 : 31;  // 1..31
+#else
+        const uint32_t z = x[0] ? (uint32_t)__builtin_ctz(x[0]) : 31;
+#endif
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = (x[i] >> z) | (x[i + 1] << (32 - z));
+        x[7] >>= z;
+#pragma unroll
+        for (int i = 7; i > 0; --i) y[i] = (y[i] << z) | (y[i - 1] >> (32 - z));
+        y[0] <<= z;
+        k += z;
+    }
+}
+
 // Modular inverse: Kaliski's "almost Montgomery inverse" on the Montgomery REPRESENTATIVE a~ = aR — every step is a
 // shift of u or v and a shift of r or s (no modular correction inside the loop), k in [254, 508] steps — gives
 // a~^-1 2^k = a^-1 R^-1 2^k; multiplying by 2^(512 - k) lands on a^-1 R, the Montgomery form of the inverse.  0 -> 0.
@@ -532,27 +550,29 @@ __host__ __device__ __noinline__ fp_t fp_inv(const fp_t a) {
         s[i] = (i == 0);
     }
     uint32_t k = 0;
-    // invariants (Kaliski 1995): a~ r == -u 2^k, a~ s == v 2^k (mod p); r, s < 2p < 2^255
+    // invariants (Kaliski 1995): a~ r == -u 2^k, a~ s == v 2^k (mod p); r, s < 2p < 2^255.
+    // The textbook loop does one halving per step (u even: u/2, 2s | v even: v/2, 2r | u > v: (u-v)/2, r+s, 2s |
+    // else (v-u)/2, s+r, 2r).  Here u and v are kept ODD: after a subtraction ALL trailing zeros go at once (the same
+    // sequence of textbook steps, merged), which halves the number of iterations and drops the per-step parity tests.
+    strip_zeros8(v, r, k);  // (r = 0: only v and k change)
     for (;;) {
-        if ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0) break;
-        if ((u[0] & 1) == 0) {
-            shr1_8(u, 0);
-            shl1_8(s);
-        } else if ((v[0] & 1) == 0) {
-            shr1_8(v, 0);
-            shl1_8(r);
-        } else if (!geq8(v, u)) {  // u > v
-            sub8(u, u, v);
-            shr1_8(u, 0);
+        uint32_t t[8];
+        uint32_t borrow = sub8(t, u, v);
+        if (!borrow && (t[0] | t[1] | t[2] | t[3] | t[4] | t[5] | t[6] | t[7]) != 0) {  // u > v
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = t[i];
             add8(r, r, s);
-            shl1_8(s);
+            strip_zeros8(u, s, k);
         } else {
             sub8(v, v, u);
-            shr1_8(v, 0);
             add8(s, s, r);
-            shl1_8(r);
+            if ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0) {  // u == v: the textbook's last step
+                shl1_8(r);
+                ++k;
+                break;
+            }
+            strip_zeros8(v, r, k);
         }
-        ++k;
     }
     if (geq8(r, pl)) sub8(r, r, pl);
     sub8(r, pl, r);  // r = a~^-1 2^k mod p, in [1, p]

@@ -18,7 +18,7 @@ struct sha256_ctx {
 VK_HD uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
 
 // out of line: the fully unrolled 64 rounds are ~4 KB of code and the transcript kernels call it from many sites
-__host__ __device__ __noinline__ inline void sha256_compress(uint32_t h[8], const uint8_t* blk) {
+__host__ __device__ __noinline__ inline void sha256_compress_words(uint32_t h[8], const uint32_t blk[16]) {
     const uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
         0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
@@ -29,8 +29,7 @@ __host__ __device__ __noinline__ inline void sha256_compress(uint32_t h[8], cons
         0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
     uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+    for (int i = 0; i < 16; ++i) w[i] = blk[i];
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
@@ -53,6 +52,14 @@ __host__ __device__ __noinline__ inline void sha256_compress(uint32_t h[8], cons
         hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+__host__ __device__ inline void sha256_compress(uint32_t h[8], const uint8_t* blk) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+    sha256_compress_words(h, w);
 }
 
 VK_HD void sha256_init(sha256_ctx& c) {
@@ -102,39 +109,87 @@ __host__ __device__ inline void sha256_final(sha256_ctx& c, uint8_t out[32]) {
 // single constant; RFC 9380 vectors are checked in tests/host with z_pad_len = 64.
 static const uint32_t ARK04_Z_PAD_LEN = 48;
 
+// big-endian word i of a 64-byte block held as bytes in 16 aligned words
+VK_HD uint32_t be_word(const uint32_t* blk_words, int i) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(blk_words[i], 0, 0x0123);
+#else
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(blk_words + i);
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+#endif
+}
+// copy the part of the segment [seg0, seg1) (bytes src[0 .. seg1 - seg0)) that falls into the block starting at `base`
+VK_HD void blk_copy(uint8_t* blk, uint32_t base, uint32_t seg0, uint32_t seg1, const uint8_t* src) {
+    uint32_t lo = seg0 > base ? seg0 : base, hi = seg1 < base + 64 ? seg1 : base + 64;
+    for (uint32_t q = lo; q < hi; ++q) blk[q - base] = src[q - seg0];
+}
+VK_HD void blk_put(uint8_t* blk, uint32_t base, uint32_t pos, uint32_t byte) {
+    if (pos >= base && pos < base + 64) blk[pos - base] = (uint8_t)byte;
+}
+
+// expand_message_xmd (RFC 9380 5.3.1) for 48 output bytes = b1 || b2[0..16), on 32-bit words.  On the device a
+// byte-at-a-time SHA update (one buffer-full test and one length update per byte) is a chain of branches and
+// local-memory round trips, ~90 cycles per byte for a lone thread — more than the compressions themselves.  Here every
+// 64-byte block is zeroed, filled by a few straight segment copies, and read back as words; b1 / b2 take b0 (and
+// b0 ^ b1) from the state words.
+__host__ __device__ inline void xmd48_words(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len,
+                                            uint32_t z_pad_len, uint32_t b1[8], uint32_t b2[8]) {
+    const uint32_t IV[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    // b0 = H(Z_pad || msg || I2OSP(48, 2) || I2OSP(0, 1) || DST || I2OSP(len(DST), 1))
+    const uint32_t m0 = z_pad_len, m1 = m0 + msg_len, d0 = m1 + 3, d1 = d0 + dst_len, total = d1 + 1;
+    const uint32_t nblk = (total + 9 + 63) / 64;
+    uint32_t b0[8], w[16], bw[16];
+    uint8_t* bb = reinterpret_cast<uint8_t*>(bw);
+    for (int i = 0; i < 8; ++i) b0[i] = IV[i];
+    for (uint32_t blk = 0; blk < nblk; ++blk) {
+        const uint32_t base = blk * 64;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bw[i] = 0;
+        blk_copy(bb, base, m0, m1, msg);
+        blk_put(bb, base, m1 + 1, 48);
+        blk_copy(bb, base, d0, d1, dst);
+        blk_put(bb, base, d1, dst_len);
+        blk_put(bb, base, total, 0x80);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = be_word(bw, i);
+        if (blk == nblk - 1) w[15] = total * 8;  // (message lengths here are far below 2^29 bytes)
+        sha256_compress_words(b0, w);
+    }
+    // b_i = H(strxor(b0, b_(i-1)) || I2OSP(i, 1) || DST || I2OSP(len(DST), 1)),  b_0' = 0  (one block for DSTs <= 21 bytes)
+    const uint32_t tl = 32 + 1 + dst_len + 1, tblk = (tl + 9 + 63) / 64;
+    for (int round = 1; round <= 2; ++round) {
+        uint32_t* out = round == 1 ? b1 : b2;
+        uint32_t h[8];
+        for (int i = 0; i < 8; ++i) h[i] = IV[i];
+        for (uint32_t blk = 0; blk < tblk; ++blk) {
+            const uint32_t base = blk * 64;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bw[i] = 0;
+            blk_put(bb, base, 32, (uint32_t)round);
+            blk_copy(bb, base, 33, 33 + dst_len, dst);
+            blk_put(bb, base, 33 + dst_len, dst_len);
+            blk_put(bb, base, tl, 0x80);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = be_word(bw, i);
+            if (blk == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = round == 1 ? b0[i] : (b0[i] ^ b1[i]);
+            }
+            if (blk == tblk - 1) w[15] = tl * 8;
+            sha256_compress_words(h, w);
+        }
+        for (int i = 0; i < 8; ++i) out[i] = h[i];
+    }
+}
+
 __host__ __device__ inline void expand_message_xmd48(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len,
                                                      uint32_t z_pad_len, uint8_t out[48]) {
-    uint8_t dlen = (uint8_t)dst_len;
-    uint8_t b0[32], b1[32], b2[32], t[3];
-    sha256_ctx c;
-    sha256_init(c);
-    sha256_update_zeros(c, z_pad_len);
-    sha256_update(c, msg, msg_len);
-    t[0] = 0; t[1] = 48; t[2] = 0;  // I2OSP(48, 2) || I2OSP(0, 1)
-    sha256_update(c, t, 3);
-    sha256_update(c, dst, dst_len);
-    sha256_update(c, &dlen, 1);
-    sha256_final(c, b0);
-
-    sha256_init(c);
-    sha256_update(c, b0, 32);
-    t[0] = 1;
-    sha256_update(c, t, 1);
-    sha256_update(c, dst, dst_len);
-    sha256_update(c, &dlen, 1);
-    sha256_final(c, b1);
-
-    uint8_t x[32];
-    for (int i = 0; i < 32; ++i) x[i] = b0[i] ^ b1[i];
-    sha256_init(c);
-    sha256_update(c, x, 32);
-    t[0] = 2;
-    sha256_update(c, t, 1);
-    sha256_update(c, dst, dst_len);
-    sha256_update(c, &dlen, 1);
-    sha256_final(c, b2);
-    for (int i = 0; i < 32; ++i) out[i] = b1[i];
-    for (int i = 0; i < 16; ++i) out[32 + i] = b2[i];
+    uint32_t b1[8], b2[8];
+    xmd48_words(msg, msg_len, dst, dst_len, z_pad_len, b1, b2);
+    for (int i = 0; i < 8; ++i)
+        for (int k = 0; k < 4; ++k) out[4 * i + k] = (uint8_t)(b1[i] >> (24 - 8 * k));
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 4; ++k) out[32 + 4 * i + k] = (uint8_t)(b2[i] >> (24 - 8 * k));
 }
 
 // Fr (Montgomery) from 48 big-endian bytes, reduced mod r:  v = hi * 2^256 + lo
@@ -158,10 +213,24 @@ __host__ __device__ inline fp_t fr_from_be48(const uint8_t u[48]) {
     return fp_add<S>(fp_mul_ni<S>(r2, lo), fp_mul_ni<S>(r3, hi));
 }
 
+// the same from the big-endian words of b1 || b2[0..4): hi = b1[0..4), lo = b1[4..8) || b2[0..4)
+__host__ __device__ inline fp_t fr_from_be48_words(const uint32_t b1[8], const uint32_t b2[8]) {
+    const uint32_t R3[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+    fp_t hi, lo, r2, r3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r2.l[i] = S::r2(i);
+        r3.l[i] = R3[i];
+        hi.l[i] = i < 4 ? b1[3 - i] : 0;
+        lo.l[i] = i < 4 ? b2[3 - i] : b1[11 - i];
+    }
+    return fp_add<S>(fp_mul_ni<S>(r2, lo), fp_mul_ni<S>(r3, hi));
+}
+
 __host__ __device__ inline fp_t hash_to_fr(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
-    uint8_t u[48];
-    expand_message_xmd48(msg, msg_len, dst, dst_len, ARK04_Z_PAD_LEN, u);
-    return fr_from_be48(u);
+    uint32_t b1[8], b2[8];
+    xmd48_words(msg, msg_len, dst, dst_len, ARK04_Z_PAD_LEN, b1, b2);
+    return fr_from_be48_words(b1, b2);
 }
 
 // Fr -> 32 little-endian canonical bytes (ark-serialize)
@@ -208,7 +277,10 @@ struct transcript_t {
 };
 
 __host__ __device__ inline void tr_append_raw(transcript_t& t, const uint8_t* p, uint32_t n) {
-    for (uint32_t i = 0; i < n && t.len < TR_MAX; ++i) t.state[t.len++] = p[i];
+    const uint32_t at = t.len, room = TR_MAX - at;
+    if (n > room) n = room;
+    for (uint32_t i = 0; i < n; ++i) t.state[at + i] = p[i];
+    t.len = at + n;
 }
 __host__ __device__ inline void tr_append_label(transcript_t& t, const char* label) {
     for (const char* p = label; *p; ++p)

@@ -231,10 +231,14 @@ static int32_t launch_fold_scalars(vkzg_ctx* ctx, IpaState st, uint64_t B, uint3
 }
 
 // L, R -> affine (one inversion), outputs, transcript, challenge (ipa/mod.rs:301-306)
+// SOLO (a handful of proofs): one thread per CTA, its own inversion — the shuffle scans of the shared inversion are ten
+// products on the critical path that buy nothing when the other lanes are idle.
+template <bool SOLO>
 __global__ void __launch_bounds__(64) k_ipa_challenge(IpaState st, uint64_t B, uint32_t round, uint32_t rounds,
                                                       affine_t* __restrict__ L_out, affine_t* __restrict__ R_out) {
-    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = p < B;  // (no early return before the warp-wide inversion)
+    uint64_t p = SOLO ? (uint64_t)blockIdx.x : (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < B && (!SOLO || threadIdx.x == 0);  // (no early return before the warp-wide inversion)
+    if (SOLO && !live) return;
     xyzz_t l = xyzz_inf(), r = xyzz_inf();
     if (live) {
         l = st.lr[2 * p];
@@ -242,7 +246,8 @@ __global__ void __launch_bounds__(64) k_ipa_challenge(IpaState st, uint64_t B, u
     }
     bool linf = xyzz_is_inf(l), rinf = xyzz_is_inf(r);
     fp_t zl = linf ? fp_one<Q>() : l.zzz, zr = rinf ? fp_one<Q>() : r.zzz;
-    fp_t inv = warp_inverse_of_lane_products_t<Q>(fp_mul_ni<Q>(zl, zr));  // the 64 points of a warp share one inversion
+    // (batches: the 64 points of a warp share one inversion)
+    fp_t inv = SOLO ? fp_inv<Q>(fp_mul_ni<Q>(zl, zr)) : warp_inverse_of_lane_products_t<Q>(fp_mul_ni<Q>(zl, zr));
     if (!live) return;
     affine_t la = linf ? affine_inf() : xyzz_to_affine_with_inv(l, fp_mul_ni<Q>(inv, zr));
     affine_t ra = rinf ? affine_inf() : xyzz_to_affine_with_inv(r, fp_mul_ni<Q>(inv, zl));
@@ -340,7 +345,10 @@ static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint3
         uint32_t m = N >> (r + 1);
         VK_TRY(launch_fold_scalars(ctx, st, B, N, r ? 2 * m : 0, m, T, with_b, nullptr));
         VK_TRY(fixed_base_msm(ctx, k, sc, T, 2 * B, m, with_b ? k.n : 0xffffffffu, lr));
-        k_ipa_challenge<<<ceil_div_u64(B, 64), 64, 0, s>>>(st, B, r, rounds, d_L, d_R);
+        if (B <= 64)
+            k_ipa_challenge<true><<<(uint32_t)B, 32, 0, s>>>(st, B, r, rounds, d_L, d_R);
+        else
+            k_ipa_challenge<false><<<ceil_div_u64(B, 64), 64, 0, s>>>(st, B, r, rounds, d_L, d_R);
         VK_TRY(launch_check(ctx));
     }
     return launch_fold_scalars(ctx, st, B, N, 1, 0, T, with_b, d_tip);
