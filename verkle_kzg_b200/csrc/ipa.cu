@@ -363,81 +363,115 @@ static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint3
 //                                                               + sum_r (x_r^2 prod_{j>r} x_j) R_r
 // with s_i = prod_r (x_r if bit (rounds-1-r) of i is 0), exactly the doubling loop at :349-353.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_ipa_verify_scalars(uint64_t B, uint32_t N, uint32_t rounds, const affine_t* __restrict__ C,
-                                                           const fp_t* __restrict__ points, const fp_t* __restrict__ y,
-                                                           const fp_t* __restrict__ tip, const affine_t* __restrict__ L,
-                                                           const affine_t* __restrict__ R, const fp_t* __restrict__ b, TrPrefix pre,
-                                                           fp_t* __restrict__ fixed_sc /*[B][N+1]*/, fp_t* __restrict__ var_sc /*[B][1+2 rounds]*/) {
-    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
-    transcript_t t;
-    t.len = 0;
-    tr_append_raw(t, pre.bytes, pre.len);
-    t.dst_len = pre.dst_len;
-    for (uint32_t i = 0; i < pre.dst_len; ++i) t.dst[i] = pre.dst[i];
-    affine_t c;
-    c.x = fp_load(&C[p].x);
-    c.y = fp_load(&C[p].y);
-    fp_t yy = fp_load(y + p), tp = fp_load(tip + p);
-    tr_append_point(t, c, "C");
-    tr_append_fr(t, fp_load(points + p), "input point");
-    tr_append_fr(t, yy, "output point");
-    fp_t w = tr_digest(t, "w");
+// Warp per proof: lane 0 replays the transcript (the challenges are a sequential hash chain); then every lane builds a
+// contiguous block of s — the first log2(32) rounds select the block (one product per zero bit of the lane index), the
+// remaining rounds are the reference's doubling loop (:349-353) inside the block — and its share of <b, s>.
+__global__ void __launch_bounds__(128) k_ipa_verify_scalars(uint64_t B, uint32_t N, uint32_t rounds, const affine_t* __restrict__ C,
+                                                            const fp_t* __restrict__ points, const fp_t* __restrict__ y,
+                                                            const fp_t* __restrict__ tip, const affine_t* __restrict__ L,
+                                                            const affine_t* __restrict__ R, const fp_t* __restrict__ b, TrPrefix pre,
+                                                            fp_t* __restrict__ fixed_sc /*[B][N+1]*/, fp_t* __restrict__ var_sc /*[B][1+2 rounds]*/) {
+    __shared__ fp_t xs_sh[4][17];  // per warp: x_0 .. x_{rounds-1}, then w
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t p = (uint64_t)blockIdx.x * 4 + warp;
+    if (p >= B) return;  // (whole warps leave; only __syncwarp below)
     fp_t* fs = fixed_sc + p * (N + 1);
     fp_t* vs = var_sc + p * (1 + 2 * rounds);
-    // challenges; s built by the doubling loop in place: after round r the first 2^(r+1) entries are valid
-    fp_store(fs, fp_one<S>());
-    fp_t xs[16];
-    for (uint32_t r = 0; r < rounds; ++r) {
-        affine_t l, rr;
-        l.x = fp_load(&L[p * rounds + r].x);
-        l.y = fp_load(&L[p * rounds + r].y);
-        rr.x = fp_load(&R[p * rounds + r].x);
-        rr.y = fp_load(&R[p * rounds + r].y);
-        tr_append_point(t, l, "L");
-        tr_append_point(t, rr, "R");
-        fp_t x = tr_digest(t, "x");
-        xs[r] = x;
-        uint32_t len = 1u << r;
-        for (uint32_t i = len; i-- > 0;) {
-            fp_t v = fp_load(fs + i);
-            fp_store(fs + 2 * i + 1, v);
-            fp_store(fs + 2 * i, fp_mul_ni<S>(v, x));
+    const fp_t yy = fp_load(y + p), tp = fp_load(tip + p);
+    if (lane == 0) {
+        transcript_t t;
+        t.len = 0;
+        tr_append_raw(t, pre.bytes, pre.len);
+        t.dst_len = pre.dst_len;
+        for (uint32_t i = 0; i < pre.dst_len; ++i) t.dst[i] = pre.dst[i];
+        affine_t c;
+        c.x = fp_load(&C[p].x);
+        c.y = fp_load(&C[p].y);
+        tr_append_point(t, c, "C");
+        tr_append_fr(t, fp_load(points + p), "input point");
+        tr_append_fr(t, yy, "output point");
+        xs_sh[warp][16] = tr_digest(t, "w");
+        for (uint32_t r = 0; r < rounds; ++r) {
+            affine_t l, rr;
+            l.x = fp_load(&L[p * rounds + r].x);
+            l.y = fp_load(&L[p * rounds + r].y);
+            rr.x = fp_load(&R[p * rounds + r].x);
+            rr.y = fp_load(&R[p * rounds + r].y);
+            tr_append_point(t, l, "L");
+            tr_append_point(t, rr, "R");
+            xs_sh[warp][r] = tr_digest(t, "x");
         }
     }
-    // <b, s>, then s_i <- tip * s_i
+    __syncwarp();
+    // s: lanes_used blocks of `per` consecutive entries
+    uint32_t top = rounds < 5 ? rounds : 5;
+    const uint32_t lanes_used = 1u << top, per = N >> top;
     fp_t cb = fp_zero<S>();
-    for (uint32_t i = 0; i < N; ++i) {
-        fp_t si = fp_load(fs + i);
-        cb = fp_add<S>(cb, fp_mul_ni<S>(fp_load(b + p * N + i), si));
-        fp_store(fs + i, fp_mul_ni<S>(si, tp));
+    if (lane < lanes_used) {
+        fp_t v0 = fp_one<S>();
+        for (uint32_t r = 0; r < top; ++r)
+            if (((lane >> (top - 1 - r)) & 1) == 0) v0 = fp_mul_ni<S>(v0, xs_sh[warp][r]);
+        fp_t* blk = fs + (uint64_t)lane * per;
+        fp_store(blk, v0);
+        for (uint32_t r = top; r < rounds; ++r) {
+            const fp_t x = xs_sh[warp][r];
+            uint32_t len = 1u << (r - top);
+            for (uint32_t i = len; i-- > 0;) {
+                fp_t v = fp_load(blk + i);
+                fp_store(blk + 2 * i + 1, v);
+                fp_store(blk + 2 * i, fp_mul_ni<S>(v, x));
+            }
+        }
+        // <b, s>, then s_i <- tip * s_i
+        const fp_t* bb = b + p * N + (uint64_t)lane * per;
+        for (uint32_t i = 0; i < per; ++i) {
+            fp_t si = fp_load(blk + i);
+            cb = fp_add<S>(cb, fp_mul_ni<S>(fp_load(bb + i), si));
+            fp_store(blk + i, fp_mul_ni<S>(si, tp));
+        }
     }
+    cb = warp_sum_fr(cb);
+    if (lane != 0) return;
     // suffix products prod_{j>r} x_j
     fp_t suf = fp_one<S>();
     for (uint32_t r = rounds; r-- > 0;) {
-        fp_store(vs + 1 + r, suf);                                                  // L_r
-        fp_store(vs + 1 + rounds + r, fp_mul_ni<S>(fp_mul_ni<S>(xs[r], xs[r]), suf));  // R_r
-        suf = fp_mul_ni<S>(suf, xs[r]);
+        const fp_t x = xs_sh[warp][r];
+        fp_store(vs + 1 + r, suf);                                            // L_r
+        fp_store(vs + 1 + rounds + r, fp_mul_ni<S>(fp_mul_ni<S>(x, x), suf));  // R_r
+        suf = fp_mul_ni<S>(suf, x);
     }
     fp_store(vs, suf);  // C
+    const fp_t w = xs_sh[warp][16];
     fp_t qs = fp_sub<S>(fp_mul_ni<S>(fp_mul_ni<S>(w, tp), cb), fp_mul_ni<S>(fp_mul_ni<S>(w, yy), suf));
     fp_store(fs + N, qs);
 }
 
-// variable-base double-and-add, thread per (proof, point)
+// variable-base double-and-add over the proof's own points C, L_r, R_r.  QUAD = false: a thread per (proof, point), for
+// batches that fill the GPU; QUAD = true: four lanes per (proof, point) (warp_util.cuh) — a handful of verifications last
+// as long as ONE scalar multiplication, whose dependent chain the quad routines cut from 19 to 7 products per bit.
+template <bool QUAD>
 __global__ void __launch_bounds__(128) k_var_scalar_mul(uint64_t B, uint32_t rounds, const affine_t* __restrict__ C,
                                                         const affine_t* __restrict__ L, const affine_t* __restrict__ R,
                                                         const fp_t* __restrict__ var_sc, xyzz_t* __restrict__ out) {
     const uint32_t per = 1 + 2 * rounds;
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * per) return;
-    uint64_t p = t / per;
-    uint32_t j = (uint32_t)(t % per);
-    const affine_t* src = j == 0 ? C + p : (j <= rounds ? L + p * rounds + (j - 1) : R + p * rounds + (j - 1 - rounds));
-    affine_t P;
-    P.x = fp_load(&src->x);
-    P.y = fp_load(&src->y);
-    fp_t k = fp_from_mont<S>(fp_load(var_sc + t));
+    uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> (QUAD ? 2 : 0);
+    const bool live = t < B * per;
+    if (!QUAD && !live) return;  // (QUAD: no early return, the quad routines shuffle across the whole warp)
+    affine_t P = affine_inf();
+    fp_t k = fp_zero<S>();
+    if (live) {
+        uint64_t p = t / per;
+        uint32_t j = (uint32_t)(t % per);
+        const affine_t* src = j == 0 ? C + p : (j <= rounds ? L + p * rounds + (j - 1) : R + p * rounds + (j - 1 - rounds));
+        P.x = fp_load(&src->x);
+        P.y = fp_load(&src->y);
+        k = fp_from_mont<S>(fp_load(var_sc + t));
+    }
+    if (QUAD) {
+        xyzz_t acc = var_mul_quad(P, k);
+        if (live && (threadIdx.x & 3) == 0) out[t] = acc;
+        return;
+    }
     xyzz_t acc = xyzz_inf();
 #pragma unroll 1
     for (int bit = 253; bit >= 0; --bit) {
@@ -451,12 +485,17 @@ __global__ void __launch_bounds__(128) k_var_scalar_mul(uint64_t B, uint32_t rou
     out[t] = acc;
 }
 
-__global__ void __launch_bounds__(64) k_ipa_verify_final(uint64_t B, uint32_t per, const xyzz_t* __restrict__ fixed,
-                                                         const xyzz_t* __restrict__ var, int32_t* __restrict__ ok) {
-    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
+// warp per proof: the 1 + 2 log2 N variable-base products are summed by a shuffle tree (per <= 33: one pass of 32 + a tail)
+__global__ void __launch_bounds__(128) k_ipa_verify_final(uint64_t B, uint32_t per, const xyzz_t* __restrict__ fixed,
+                                                          const xyzz_t* __restrict__ var, int32_t* __restrict__ ok) {
+    uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (p >= B) return;  // (whole warps)
     xyzz_t v = xyzz_inf();
-    for (uint32_t j = 0; j < per; ++j) v = xyzz_add_ni(v, var[p * per + j]);
+    for (uint32_t j = lane; j < per; j += 32) v = xyzz_add_ni(v, var[p * per + j]);
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) v = xyzz_add_pair(v, off);
+    if (lane != 0) return;
     xyzz_t f = fixed[p];
     bool fi = xyzz_is_inf(f), vi = xyzz_is_inf(v);
     bool eq;
@@ -487,12 +526,15 @@ int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_points, const
     VK_TRY(V.alloc(ctx, B * per));
     cudaStream_t s = ctx->stream;
     VK_TRY(barycentric_batch(ctx, k, d_points, B, b));
-    k_ipa_verify_scalars<<<ceil_div_u64(B, 64), 64, 0, s>>>(B, N, rounds, d_C, d_points, d_y, d_tip, d_L, d_R, b, pre, fs, vs);
+    k_ipa_verify_scalars<<<ceil_div_u64(B, 4), 128, 0, s>>>(B, N, rounds, d_C, d_points, d_y, d_tip, d_L, d_R, b, pre, fs, vs);
     VK_TRY(launch_check(ctx));
     VK_TRY(fixed_base_msm(ctx, k, fs, N + 1, B, 0, 0xffffffffu, F));
-    k_var_scalar_mul<<<ceil_div_u64(B * per, 128), 128, 0, s>>>(B, rounds, d_C, d_L, d_R, vs, V);
+    if (B * per <= (uint64_t)ctx->sm_count * 64)
+        k_var_scalar_mul<true><<<ceil_div_u64(B * per * 4, 128), 128, 0, s>>>(B, rounds, d_C, d_L, d_R, vs, V);
+    else
+        k_var_scalar_mul<false><<<ceil_div_u64(B * per, 128), 128, 0, s>>>(B, rounds, d_C, d_L, d_R, vs, V);
     VK_TRY(launch_check(ctx));
-    k_ipa_verify_final<<<ceil_div_u64(B, 64), 64, 0, s>>>(B, per, F, V, d_ok);
+    k_ipa_verify_final<<<ceil_div_u64(B * 32, 128), 128, 0, s>>>(B, per, F, V, d_ok);
     return launch_check(ctx);
 }
 

@@ -208,6 +208,23 @@ __global__ void __launch_bounds__(128) k_var_mul(const affine_t* __restrict__ pt
     out[t] = acc;
 }
 
+// the same with four lanes per point (warp_util.cuh): a few thousand points do not fill the GPU with one thread each and
+// the launch lasts as long as ONE scalar multiplication, so the dependent chain is what to shorten
+__global__ void __launch_bounds__(128) k_var_mul_quad(const affine_t* __restrict__ pts, const fp_t* __restrict__ sc, uint64_t n,
+                                                      xyzz_t* __restrict__ out) {
+    uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = t < n;  // (no early return: the quad routines shuffle across the whole warp)
+    affine_t P = affine_inf();
+    fp_t k = fp_zero<S>();
+    if (live) {
+        P.x = fp_load(&pts[t].x);
+        P.y = fp_load(&pts[t].y);
+        k = fp_from_mont<S>(fp_load(sc + t));
+    }
+    xyzz_t acc = var_mul_quad(P, k);
+    if (live && (threadIdx.x & 3) == 0) out[t] = acc;
+}
+
 __global__ void __launch_bounds__(256) k_xyzz_tree(const xyzz_t* __restrict__ pts, uint64_t n, xyzz_t* __restrict__ out) {
     __shared__ xyzz_t sh[256];
     xyzz_t acc = xyzz_inf();
@@ -226,7 +243,10 @@ int32_t var_base_msm(vkzg_ctx* ctx, const affine_t* d_points, const fp_t* d_scal
     VK_TRY(prod.alloc(ctx, n));
     uint32_t blocks = n > 256 * 8 ? 64 : 1;
     VK_TRY(part.alloc(ctx, blocks + 1));
-    if (n) {
+    if (n && n <= (uint64_t)ctx->sm_count * 64) {  // latency-bound: four lanes per point
+        k_var_mul_quad<<<ceil_div_u64(n * 4, 128), 128, 0, ctx->stream>>>(d_points, d_scalars, n, prod);
+        VK_TRY(launch_check(ctx));
+    } else if (n) {
         k_var_mul<<<ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(d_points, d_scalars, n, prod);
         VK_TRY(launch_check(ctx));
     }

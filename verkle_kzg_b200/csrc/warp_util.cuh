@@ -114,4 +114,88 @@ static __device__ __noinline__ xyzz_t xyzz_add_pair(const xyzz_t mine, int off) 
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Variable-base scalar multiplication in latency mode: FOUR lanes per point.
+// k P needs ~254 dependent doublings whatever the algorithm; a lone thread spends 9 multiplier latencies per
+// doubling and 10 per mixed addition.  The products of one doubling have dependency depth 3 and of one mixed
+// addition depth 4, so four lanes holding the same accumulator compute one product each per level and
+// exchange the results inside their quad (width-4 shuffles): 3 + 4 latencies per bit instead of 19.
+// All 32 lanes of a warp must call these (full-mask shuffles); special cases are resolved after the last shuffle.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ fp_t quad_get(const fp_t& v, int q) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], q, 4);
+    return r;
+}
+// fp_sel over four choices by the lane's position in its quad
+__device__ __forceinline__ fp_t quad_pick(int q, const fp_t& a0, const fp_t& a1, const fp_t& a2, const fp_t& a3) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = q == 0 ? a0.l[i] : q == 1 ? a1.l[i] : q == 2 ? a2.l[i] : a3.l[i];
+    return r;
+}
+
+// 2 * acc (dbl-2008-s-1, a = 0): levels {V = U^2, XX = X^2}, {W = U V, S = X V, MM = M^2, ZZ3 = V ZZ}, {Y3a, Y3b, ZZZ3}
+static __device__ __noinline__ xyzz_t xyzz_dbl_quad(const xyzz_t p) {
+    const int q = threadIdx.x & 3;
+    const fp_t U = fp_dbl<Q>(p.y);
+    const fp_t sq = (q & 1) ? p.x : U;
+    const fp_t l1 = fp_mul_ni<Q>(sq, sq);
+    const fp_t V = quad_get(l1, 0), XX = quad_get(l1, 1);
+    const fp_t M = fp_add<Q>(fp_dbl<Q>(XX), XX);
+    const fp_t l2 = fp_mul_ni<Q>(quad_pick(q, U, p.x, M, V), quad_pick(q, V, V, M, p.zz));
+    const fp_t W = quad_get(l2, 0), Sx = quad_get(l2, 1), MM = quad_get(l2, 2);
+    xyzz_t r;
+    r.zz = quad_get(l2, 3);
+    r.x = fp_sub<Q>(MM, fp_dbl<Q>(Sx));
+    const fp_t l3 = fp_mul_ni<Q>(quad_pick(q, M, W, W, W), quad_pick(q, fp_sub<Q>(Sx, r.x), p.y, p.zzz, p.zzz));
+    r.y = fp_sub<Q>(quad_get(l3, 0), quad_get(l3, 1));
+    r.zzz = quad_get(l3, 2);
+    return xyzz_is_inf(p) ? p : r;
+}
+
+// acc + P (madd-2008-s): levels {U2 = x2 ZZ, S2 = y2 ZZZ}, {PP = P^2, RR = R^2}, {PPP = P PP, Q = X PP, ZZ3 = ZZ PP},
+// {Y3a = R (Q - X3), Y3b = Y PPP, ZZZ3 = ZZZ PPP}
+static __device__ __noinline__ xyzz_t xyzz_madd_quad(const xyzz_t acc, const affine_t pt) {
+    const int q = threadIdx.x & 3;
+    const fp_t l1 = fp_mul_ni<Q>((q & 1) ? pt.y : pt.x, (q & 1) ? acc.zzz : acc.zz);
+    const fp_t U2 = quad_get(l1, 0), S2 = quad_get(l1, 1);
+    const fp_t P = fp_sub<Q>(U2, acc.x), R = fp_sub<Q>(S2, acc.y);
+    const fp_t sq = (q & 1) ? R : P;
+    const fp_t l2 = fp_mul_ni<Q>(sq, sq);
+    const fp_t PP = quad_get(l2, 0), RR = quad_get(l2, 1);
+    const fp_t l3 = fp_mul_ni<Q>(quad_pick(q, P, acc.x, acc.zz, acc.zz), PP);
+    const fp_t PPP = quad_get(l3, 0), Qv = quad_get(l3, 1);
+    xyzz_t r;
+    r.zz = quad_get(l3, 2);
+    r.x = fp_sub<Q>(fp_sub<Q>(RR, PPP), fp_dbl<Q>(Qv));
+    const fp_t l4 = fp_mul_ni<Q>(quad_pick(q, R, acc.y, acc.zzz, acc.zzz), quad_pick(q, fp_sub<Q>(Qv, r.x), PPP, PPP, PPP));
+    r.y = fp_sub<Q>(quad_get(l4, 0), quad_get(l4, 1));
+    r.zzz = quad_get(l4, 2);
+    if (affine_is_inf(pt)) return acc;
+    if (xyzz_is_inf(acc)) return xyzz_from_affine(pt);
+    if (fp_is_zero(P)) return fp_is_zero(R) ? xyzz_dbl_affine(pt) : xyzz_inf();
+    return r;
+}
+
+// k * P for the quad's point (all four lanes pass the same P and the same canonical scalar); MSB-first double-and-add
+static __device__ __noinline__ xyzz_t var_mul_quad(const affine_t P, const fp_t k_canon) {
+    xyzz_t acc = xyzz_inf();
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; --bit) {
+        acc = xyzz_dbl_quad(acc);
+        uint32_t limb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i == (bit >> 5)) limb = k_canon.l[i];
+        const bool set = (limb >> (bit & 31)) & 1;
+        if (__any_sync(0xffffffffu, set)) {  // (warp-uniform branch: the shuffles inside need every lane)
+            xyzz_t t = xyzz_madd_quad(acc, P);
+            if (set) acc = t;
+        }
+    }
+    return acc;
+}
+
 }  // namespace vk
