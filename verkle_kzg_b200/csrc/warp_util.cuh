@@ -179,20 +179,53 @@ static __device__ __noinline__ xyzz_t xyzz_madd_quad(const xyzz_t acc, const aff
     return r;
 }
 
-// k * P for the quad's point (all four lanes pass the same P and the same canonical scalar); MSB-first double-and-add
+// a + b, both XYZZ (add-2008-s): levels {U1, U2, S1, S2}, {PP, RR, ZZ12 = ZZ1 ZZ2, ZZZ12 = ZZZ1 ZZZ2},
+// {PPP, Q = U1 PP, ZZ3 = ZZ12 PP}, {Y3a = R (Q - X3), Y3b = S1 PPP, ZZZ3 = ZZZ12 PPP}
+static __device__ __noinline__ xyzz_t xyzz_add_quad(const xyzz_t a, const xyzz_t b) {
+    const int q = threadIdx.x & 3;
+    const fp_t l1 = fp_mul_ni<Q>(quad_pick(q, a.x, b.x, a.y, b.y), quad_pick(q, b.zz, a.zz, b.zzz, a.zzz));
+    const fp_t U1 = quad_get(l1, 0), U2 = quad_get(l1, 1), S1 = quad_get(l1, 2), S2 = quad_get(l1, 3);
+    const fp_t P = fp_sub<Q>(U2, U1), R = fp_sub<Q>(S2, S1);
+    const fp_t l2 = fp_mul_ni<Q>(quad_pick(q, P, R, a.zz, a.zzz), quad_pick(q, P, R, b.zz, b.zzz));
+    const fp_t PP = quad_get(l2, 0), RR = quad_get(l2, 1), ZZ12 = quad_get(l2, 2), ZZZ12 = quad_get(l2, 3);
+    const fp_t l3 = fp_mul_ni<Q>(quad_pick(q, P, U1, ZZ12, ZZ12), PP);
+    const fp_t PPP = quad_get(l3, 0), Qv = quad_get(l3, 1);
+    xyzz_t r;
+    r.zz = quad_get(l3, 2);
+    r.x = fp_sub<Q>(fp_sub<Q>(RR, PPP), fp_dbl<Q>(Qv));
+    const fp_t l4 = fp_mul_ni<Q>(quad_pick(q, R, S1, ZZZ12, ZZZ12), quad_pick(q, fp_sub<Q>(Qv, r.x), PPP, PPP, PPP));
+    r.y = fp_sub<Q>(quad_get(l4, 0), quad_get(l4, 1));
+    r.zzz = quad_get(l4, 2);
+    if (xyzz_is_inf(a)) return b;
+    if (xyzz_is_inf(b)) return a;
+    if (fp_is_zero(P)) return xyzz_add_ni(a, b);  // doubling / opposite points
+    return r;
+}
+
+// k * P for the quad's point (all four lanes pass the same P and the same canonical scalar k < 2^254): fixed 4-bit
+// windows, MSB first, over the table P, 2P, ..., 15P (7 doublings + 7 mixed additions to build) — per window four
+// doublings (3 levels each) and one addition (4 levels): ~1070 multiplier latencies instead of the ~4800 of a lone thread.
 static __device__ __noinline__ xyzz_t var_mul_quad(const affine_t P, const fp_t k_canon) {
+    xyzz_t T[15];
+    T[0] = xyzz_from_affine(P);
+    if (affine_is_inf(P)) T[0] = xyzz_inf();
+#pragma unroll 1
+    for (int d = 2; d <= 15; ++d) T[d - 1] = (d & 1) ? xyzz_madd_quad(T[d - 2], P) : xyzz_dbl_quad(T[d / 2 - 1]);
     xyzz_t acc = xyzz_inf();
 #pragma unroll 1
-    for (int bit = 253; bit >= 0; --bit) {
-        acc = xyzz_dbl_quad(acc);
+    for (int w = 63; w >= 0; --w) {
+        if (w != 63) {
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) acc = xyzz_dbl_quad(acc);
+        }
         uint32_t limb = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (i == (bit >> 5)) limb = k_canon.l[i];
-        const bool set = (limb >> (bit & 31)) & 1;
-        if (__any_sync(0xffffffffu, set)) {  // (warp-uniform branch: the shuffles inside need every lane)
-            xyzz_t t = xyzz_madd_quad(acc, P);
-            if (set) acc = t;
+            if (i == (w >> 3)) limb = k_canon.l[i];
+        const uint32_t d = (limb >> (4 * (w & 7))) & 15;
+        if (__any_sync(0xffffffffu, d != 0)) {  // (warp-uniform branch: the shuffles inside need every lane)
+            xyzz_t t = xyzz_add_quad(acc, T[d ? d - 1 : 0]);
+            if (d) acc = t;
         }
     }
     return acc;
