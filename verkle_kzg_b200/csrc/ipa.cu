@@ -446,9 +446,9 @@ __global__ void __launch_bounds__(128) k_ipa_verify_scalars(uint64_t B, uint32_t
     fp_store(fs + N, qs);
 }
 
-// variable-base double-and-add over the proof's own points C, L_r, R_r.  QUAD = false: a thread per (proof, point), for
-// batches that fill the GPU; QUAD = true: four lanes per (proof, point) (warp_util.cuh) — a handful of verifications last
-// as long as ONE scalar multiplication, whose dependent chain the quad routines cut from 19 to 7 products per bit.
+// variable-base scalar multiplications over the proof's own points C, L_r, R_r, 4-bit windows (warp_util.cuh).
+// QUAD = false: a thread per (proof, point), for batches that fill the GPU; QUAD = true: four lanes per (proof, point) —
+// a handful of verifications last as long as ONE scalar multiplication, whose dependent chain var_mul_quad shortens.
 template <bool QUAD>
 __global__ void __launch_bounds__(128) k_var_scalar_mul(uint64_t B, uint32_t rounds, const affine_t* __restrict__ C,
                                                         const affine_t* __restrict__ L, const affine_t* __restrict__ R,
@@ -470,19 +470,9 @@ __global__ void __launch_bounds__(128) k_var_scalar_mul(uint64_t B, uint32_t rou
     if (QUAD) {
         xyzz_t acc = var_mul_quad(P, k);
         if (live && (threadIdx.x & 3) == 0) out[t] = acc;
-        return;
+    } else {
+        out[t] = var_mul_windowed(P, k);
     }
-    xyzz_t acc = xyzz_inf();
-#pragma unroll 1
-    for (int bit = 253; bit >= 0; --bit) {
-        acc = xyzz_dbl_ni(acc);
-        uint32_t limb = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i == (bit >> 5)) limb = k.l[i];
-        if ((limb >> (bit & 31)) & 1) xyzz_madd(acc, P);
-    }
-    out[t] = acc;
 }
 
 // warp per proof: the 1 + 2 log2 N variable-base products are summed by a shuffle tree (per <= 33: one pass of 32 + a tail)

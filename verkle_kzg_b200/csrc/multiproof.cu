@@ -194,22 +194,11 @@ __global__ void __launch_bounds__(128) k_var_mul(const affine_t* __restrict__ pt
     affine_t P;
     P.x = fp_load(&pts[t].x);
     P.y = fp_load(&pts[t].y);
-    fp_t k = fp_from_mont<S>(fp_load(sc + t));
-    xyzz_t acc = xyzz_inf();
-#pragma unroll 1
-    for (int bit = 253; bit >= 0; --bit) {
-        acc = xyzz_dbl_ni(acc);
-        uint32_t limb = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i == (bit >> 5)) limb = k.l[i];
-        if ((limb >> (bit & 31)) & 1) xyzz_madd(acc, P);
-    }
-    out[t] = acc;
+    out[t] = var_mul_windowed(P, fp_from_mont<S>(fp_load(sc + t)));
 }
 
-// the same with four lanes per point (warp_util.cuh): a few thousand points do not fill the GPU with one thread each and
-// the launch lasts as long as ONE scalar multiplication, so the dependent chain is what to shorten
+// four lanes per point (var_mul_quad): a few thousand points do not fill the GPU with one thread each and the launch
+// lasts as long as ONE scalar multiplication, so the dependent chain is what to shorten
 __global__ void __launch_bounds__(128) k_var_mul_quad(const affine_t* __restrict__ pts, const fp_t* __restrict__ sc, uint64_t n,
                                                       xyzz_t* __restrict__ out) {
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;

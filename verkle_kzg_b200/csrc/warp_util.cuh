@@ -115,12 +115,43 @@ static __device__ __noinline__ xyzz_t xyzz_add_pair(const xyzz_t mine, int off) 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Variable-base scalar multiplication k P (the verifier's C, L_r, R_r and the multiproof's commitments): fixed 4-bit
+// windows, MSB first, over the table P, 2P, ..., 15P — 252 doublings + <= 64 additions instead of the 254 + ~127 of
+// double-and-add, and no data-dependent branch per bit.  One thread per point: the throughput form, for batches that fill
+// the GPU (a handful of points use var_mul_quad below).
+// ---------------------------------------------------------------------------------------------------
+static __device__ __noinline__ xyzz_t var_mul_windowed(const affine_t P, const fp_t k_canon) {
+    if (affine_is_inf(P)) return xyzz_inf();
+    xyzz_t T[15];
+    T[0] = xyzz_from_affine(P);
+#pragma unroll 1
+    for (int d = 2; d <= 15; ++d) T[d - 1] = (d & 1) ? xyzz_add_ni(T[d - 2], T[0]) : xyzz_dbl_ni(T[d / 2 - 1]);
+    xyzz_t acc = xyzz_inf();
+#pragma unroll 1
+    for (int w = 63; w >= 0; --w) {
+        if (!xyzz_is_inf(acc)) {
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) acc = xyzz_dbl_ni(acc);
+        }
+        uint32_t limb = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i == (w >> 3)) limb = k_canon.l[i];
+        const uint32_t d = (limb >> (4 * (w & 7))) & 15;
+        if (d) acc = xyzz_add_ni(acc, T[d - 1]);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Variable-base scalar multiplication in latency mode: FOUR lanes per point.
-// k P needs ~254 dependent doublings whatever the algorithm; a lone thread spends 9 multiplier latencies per
-// doubling and 10 per mixed addition.  The products of one doubling have dependency depth 3 and of one mixed
-// addition depth 4, so four lanes holding the same accumulator compute one product each per level and
-// exchange the results inside their quad (width-4 shuffles): 3 + 4 latencies per bit instead of 19.
-// All 32 lanes of a warp must call these (full-mask shuffles); special cases are resolved after the last shuffle.
+// k P needs ~252 dependent doublings whatever the algorithm, and a lone thread is a chain of dependent calls of the
+// out-of-line multiplier (~980 cycles each, tools/coop_probe.cu; inlining the products instead makes 30-50 KB of
+// straight-line code per point operation, which a lone warp cannot fetch any faster).  The products of one doubling
+// have dependency depth 3 and of one addition depth 4, so four lanes holding the same accumulator compute one product
+// each per level and exchange the results inside their quad (width-4 shuffles): measured 5.2 k cycles per doubling and
+// 9.8 k per addition against 8.8 k / 13.7 k.  All 32 lanes of a warp must call these (full-mask shuffles); special
+// cases are resolved after the last shuffle.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ fp_t quad_get(const fp_t& v, int q) {
     fp_t r;
