@@ -65,6 +65,23 @@ def test_ipa_multiproof_skewed_groups(eng):
     key.free()
 
 
+def test_ipa_multiproof_many_queries(eng):
+    """more commitments than the four-lane scalar multiplication takes (> 64 per SM): the thread-per-point windowed form"""
+    N, m = 32, 12000
+    rng = np.random.default_rng(79)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, N + 1)
+    key = eng.load_key(bases[:N], q=bases[N], window_bits=8)
+    f, C, z, y = _queries(eng, key, rng, N, m)
+    got = eng.multiproof_prove(key, "ipa", f, C, z, y)
+    assert eng.multiproof_verify_ipa(key, C, z, y, got)
+    assert orc.multiproof_verify("ipa", bases, N, C, z, y, got)
+    y2 = y.copy()
+    y2[m - 1] = orc.field_op(0, "add", y[m - 1], orc.fr_to_buf([1])[0])[0]
+    assert not eng.multiproof_verify_ipa(key, C, z, y2, got)
+    key.free()
+
+
 def test_kzg_multiproof(eng):
     N, m = 32, 20
     rng = np.random.default_rng(78)
