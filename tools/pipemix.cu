@@ -2,11 +2,13 @@
 // build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/pipemix tools/pipemix.cu
 #include <cstdio>
 #include <cstdint>
-template <int NI, int NA, int ND, int NX>  // per inner step: NI mad.wide, NA add (IADD3), ND fma.f64, NX mad.wide with carry chain (pairs)
+template <int NI, int NA, int ND, int NX, int NY = 0>  // per inner step: NI mad.wide, NA add (IADD3), ND fma.f64, NX mad.wide with carry chain (pairs),
+                                                      // NY independent wide MACs whose carry-OUT is captured by an addc into a carry word (no carry-in)
 __global__ void __launch_bounds__(256) k(uint32_t iters, uint64_t* sink) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t a[8], b[8], s[8];
     uint64_t acc[8], xacc[8];
+    uint32_t cw[8];
     double da[8], dacc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -15,6 +17,7 @@ __global__ void __launch_bounds__(256) k(uint32_t iters, uint64_t* sink) {
         s[j] = t + j;
         acc[j] = j + t;
         xacc[j] = j * 3 + t;
+        cw[j] = j;
         da[j] = 1.0 + j * 1e-9 + t * 1e-12;
         dacc[j] = j;
     }
@@ -27,6 +30,14 @@ __global__ void __launch_bounds__(256) k(uint32_t iters, uint64_t* sink) {
                 if (j < NI) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(b[(j + r) & 7]));
                 if (j < NA) asm volatile("add.u32 %0, %0, %1;" : "+r"(s[j]) : "r"(a[(j + r) & 7]));
                 if (j < ND) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(dacc[j]) : "d"(da[j]), "d"(da[(j + r) & 7]));
+            }
+#pragma unroll
+            for (int j = 0; j < NY; ++j) {
+                uint32_t lo = (uint32_t)xacc[j], hi = (uint32_t)(xacc[j] >> 32);
+                asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                             : "+r"(lo), "+r"(hi), "+r"(cw[j])
+                             : "r"(a[j]), "r"(b[(j + r) & 7]));
+                xacc[j] = ((uint64_t)hi << 32) | lo;
             }
             if (NX) {
                 uint32_t lo[4], hi[4];
@@ -47,10 +58,10 @@ __global__ void __launch_bounds__(256) k(uint32_t iters, uint64_t* sink) {
     uint64_t x = 0;
     double ds = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { x ^= acc[j] ^ s[j] ^ xacc[j]; ds += dacc[j]; }
+    for (int j = 0; j < 8; ++j) { x ^= acc[j] ^ s[j] ^ xacc[j] ^ cw[j]; ds += dacc[j]; }
     if (x == 0x123456789abcdefull || ds == 1234.5678) sink[0] = x;
 }
-template <int NI, int NA, int ND, int NX>
+template <int NI, int NA, int ND, int NX, int NY = 0>
 void run(const char* name) {
     uint64_t* sink;
     cudaMalloc(&sink, 8);
@@ -59,11 +70,11 @@ void run(const char* name) {
     cudaEventCreate(&b);
     int blocks = 148 * 4;
     uint32_t iters = 4000;
-    k<NI, NA, ND, NX><<<blocks, 256>>>(100, sink);
+    k<NI, NA, ND, NX, NY><<<blocks, 256>>>(100, sink);
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(a);
-        k<NI, NA, ND, NX><<<blocks, 256>>>(iters, sink);
+        k<NI, NA, ND, NX, NY><<<blocks, 256>>>(iters, sink);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         float ms;
@@ -85,5 +96,8 @@ int main() {
     run<0, 0, 0, 1>("carry chain of 4 wide pairs");
     run<0, 0, 8, 1>("carry chain of 4 + 8 fma.f64");
     run<0, 8, 0, 1>("carry chain of 4 + 8 add.u32");
+    run<0, 0, 0, 0, 4>("4 wide MACs, carry-out captured by addc");
+    run<0, 0, 0, 0, 8>("8 wide MACs, carry-out captured by addc");
+    run<0, 8, 0, 0, 8>("8 carry-out MACs + 8 add.u32");
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }
