@@ -209,14 +209,16 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
             const char* e = getenv("VKZG_FB_LPJ");  // tuning knob (8, 16 or 32)
             dense_lpj = e ? atoi(e) : 8;
         }
-        // minimum number of half-waves of warps: 6 for a lone launch (a 1.7-wave grid of long warps leaves the SMs idle in its
-        // tail), 3 for the IPA cross terms, whose half-batches run on two streams and fill each other's tails (measured)
+        // minimum number of half-waves of warps: 20 for a lone launch (a grid of a few waves of long warps leaves the SMs idle
+        // in its tail; with the pair-split fold the extra fold levels of whole-warp jobs cost less than that: commits at
+        // 2^14 measured 1.790 M/s with 32 lanes per job, 1.772 M/s with 16 or 8), 3 for the IPA cross terms, whose
+        // half-batches run on two streams and fill each other's tails (measured: 196.6 k proofs/s with 8 lanes, 188.2 k with 32)
         static int fill_env = -1;
         if (fill_env < 0) {
             const char* e = getenv("VKZG_FB_FILL_X2");
             fill_env = e ? atoi(e) : 0;
         }
-        const int fill_x2 = fill_env ? fill_env : (ipa_m && ctx->ipa_two_streams ? 3 : 6);
+        const int fill_x2 = fill_env ? fill_env : (ipa_m && ctx->ipa_two_streams ? 3 : 20);
         uint64_t warps16 = jobs / 2, warps8 = jobs / 4, fill = (uint64_t)ctx->sm_count * 16 * fill_x2 / 6;
         if (dense_lpj == 8 && warps8 >= 3 * fill) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, 1, d_out);
         if (dense_lpj <= 16 && warps16 >= 3 * fill) return launch_fixed_base<16>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, nullptr, nullptr, 1, d_out);
