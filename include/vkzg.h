@@ -201,6 +201,10 @@ int32_t vkzg_tree_insert(vkzg_tree* tree, const uint8_t* keys, const uint8_t* va
 /* 1 = found (value copied to value_out[32]), 0 = absent */
 int32_t vkzg_tree_get(const vkzg_tree* tree, const uint8_t* key, uint8_t* value_out);
 uint64_t vkzg_tree_nodes(const vkzg_tree* tree);
+/* root commitment (Node::gen_commitment, node.rs:212-277) of the current tree; *n_committed = node commitments recomputed by
+ * this call (0 when everything was cached).  Dirty extensions travel to the device as 65-byte records and their leaf-side
+ * rows are expanded there; all new commitments are cached back on the host.  One tree must not be committed from two
+ * threads at once (it is the caller's structure, like the reference's &mut self).                                     */
 int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* tree, vkzg_g1_affine* root_out, uint64_t* n_committed);
 
 /* ---- next row: KZG::setup (kzg/mod.rs:115-124) -------------------------------------------------------- */
