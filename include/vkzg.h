@@ -131,6 +131,11 @@ int32_t vkzg_kzg_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f /*[
 /* device-pointer variant: rows that hit the reference's panic get the identity as proof (no status) */
 int32_t vkzg_kzg_open_batch_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_f, uint32_t len, uint32_t domain_n,
                                 const vkzg_fr* d_points, uint64_t B, vkzg_g1_affine* d_proof, vkzg_fr* d_y);
+/* KZG::commit (kzg/mod.rs:126-134) + KZG::prove_point (:136-154) over the same B vectors with ONE upload of the rows (bulk
+ * callers that commit and open the same data, as benches/kzg.rs does): commitments[B], proof[B], y[B]               */
+int32_t vkzg_kzg_commit_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n,
+                                   const vkzg_fr* points, uint64_t B, vkzg_g1_affine* commitments, vkzg_g1_affine* proof,
+                                   vkzg_fr* y);
 
 /* ---- I1: IPA::prove_point + low_level_ipa (ipa/mod.rs:137-154, :268-319), batched -------------------- */
 /* a[B][N], points[B], commitments[B].  `prefix` (may be NULL) is the byte state of an in-flight transcript

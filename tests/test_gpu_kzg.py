@@ -65,6 +65,23 @@ def test_quotient_evaluate_open_match_oracle(eng, N, length, domain, wb):
     key.free()
 
 
+def test_commit_open_fused_equals_separate_calls(eng):
+    """vkzg_kzg_commit_open_batch (one upload of the rows) == vkzg_commit_batch + vkzg_kzg_open_batch, incl. the chunked path"""
+    srs, key = _key(eng, 32, 8)
+    rng = np.random.default_rng(4321)
+    for B, length in ((1, 32), (37, 20), (9000, 32)):   # 9000 >= 8192: the rows upload in pipelined chunks
+        f = orc.rand_fr_buf(rng, B * length).reshape(B, length, 32)
+        zb = orc.fr_to_buf([int(v) for v in rng.integers(0, length, B)])
+        zb[B // 2] = orc.fr_to_buf([77777])[0]               # one outside point
+        C, pf, y = eng.kzg_commit_open_batch(key, f, zb)
+        assert (C == eng.commit_batch(key, f)).all()
+        pf2, y2 = eng.kzg_open_batch(key, f, zb)
+        assert (pf == pf2).all() and (y == y2).all()
+    epf, ey, ok = orc.kzg_prove(srs, f[0], zb[0])
+    assert ok and (pf[0] == epf).all() and (y[0] == ey).all() and (C[0] == orc.msm(srs, f[0])).all()
+    key.free()
+
+
 def test_point_equal_to_key_size_is_fenced(eng):
     """quirk Q2: point == size takes the in-domain branch and indexes out of bounds in the reference"""
     from verkle_kzg_b200 import VkzgError

@@ -349,4 +349,39 @@ int32_t vkzg_kzg_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, ui
     return stream_sync(ctx);
 }
 
+// KZG::commit + KZG::prove_point for bulk callers that commit to AND open the same vectors (the reference's own bench shape,
+// benches/kzg.rs): the rows cross PCIe once, chunk by chunk under the commitment MSM of the previous chunk.
+int32_t vkzg_kzg_commit_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n,
+                                   const vkzg_fr* points, uint64_t B, vkzg_g1_affine* commitments, vkzg_g1_affine* proof, vkzg_fr* y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!f || !points || !commitments || !proof || !y))) return VKZG_ERR_ARG;
+    if (len == 0 || len > k->n) return VKZG_ERR_RANGE;
+    if (B == 0) return VKZG_OK;
+    DevBuf<fp_t> df, dp, dy;
+    DevBuf<affine_t> dc, dpr;
+    DevBuf<xyzz_t> acc;
+    VK_TRY(df.alloc(ctx, B * len));
+    VK_TRY(upload(ctx, dp, points, B));
+    VK_TRY(dc.alloc(ctx, B));
+    VK_TRY(dpr.alloc(ctx, B));
+    VK_TRY(dy.alloc(ctx, B));
+    VK_TRY(acc.alloc(ctx, B));
+    ChunkedUpload up(ctx);
+    VK_TRY(up.init());
+    const uint64_t chunk = pipeline_chunk(B);
+    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
+        uint64_t nb = B - b0 < chunk ? B - b0 : chunk;
+        VK_TRY(up.copy(df.p + b0 * len, (const fp_t*)f + b0 * len, nb * len * sizeof(fp_t)));
+        VK_TRY(up.publish());
+        VK_TRY(fixed_base_msm(ctx, *k, df.p + b0 * len, len, nb, 0, 0xffffffffu, acc.p + b0));
+    }
+    VK_TRY(normalize_points(ctx, acc, B, dc));
+    VK_TRY(kzg_open_core(ctx, *k, df, len, domain_n, dp, B, dpr, dy, true));
+    VK_TRY(download(ctx, commitments, dc.p, B));
+    VK_TRY(download(ctx, proof, dpr.p, B));
+    VK_TRY(download(ctx, y, dy.p, B));
+    return stream_sync(ctx);
+}
+
 }  // extern "C"

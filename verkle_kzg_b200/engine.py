@@ -275,6 +275,19 @@ class Engine:
                                           hptr(points), ctypes.c_uint64(B), hptr(proof), hptr(y)), "vkzg_kzg_open_batch")
         return proof, y
 
+    def kzg_commit_open_batch(self, key, f, points, domain_n=0):
+        """commit + open the same vectors with one upload of the rows -> (commitments [B,64], proof [B,64], y [B,32])"""
+        f = u8(f, 32)
+        B, ln = f.shape[0], f.shape[1]
+        points = u8(points, 32).reshape(B, 32)
+        C = np.zeros((B, 64), dtype=np.uint8)
+        proof = np.zeros((B, 64), dtype=np.uint8)
+        y = np.zeros((B, 32), dtype=np.uint8)
+        check(self._L.vkzg_kzg_commit_open_batch(self._ctx, ctypes.c_uint32(key.id), hptr(f), ctypes.c_uint32(ln), ctypes.c_uint32(domain_n),
+                                                 hptr(points), ctypes.c_uint64(B), hptr(C), hptr(proof), hptr(y)),
+              "vkzg_kzg_commit_open_batch")
+        return C, proof, y
+
     def kzg_open_batch_dev(self, key, d_f, ln, d_points, B, d_proof, d_y, domain_n=0):
         check(self._L.vkzg_kzg_open_batch_dev(self._ctx, ctypes.c_uint32(key.id), dptr(d_f), ctypes.c_uint32(ln),
                                               ctypes.c_uint32(domain_n), dptr(d_points),
