@@ -1,19 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric for the commitment hot path on B200.
+"""bench.py — BASELINE.json's metrics for the commitment hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ipa|commit|msm|kzg|multiproof|tree] [--impl reference]
+                    [--no-also] [--no-check]
 
-Default workload = BASELINE.json configs[1]: Pedersen/IPA commit + low_level_ipa proof at width 256, a batch
-of 2^14 independent vectors per GPU; one "step" = commit all vectors, then open each at a uniform in-domain
-point.  Metric: proofs/s (a proof = one committed-and-opened vector).  Under torchrun every rank runs the
-same batch size (batches shard with no data-path collective: weak scaling) and `value` is the whole-job
-aggregate over the max-over-ranks device time.
+Headline (default workload) = BASELINE.json configs[1]: Pedersen/IPA commit + low_level_ipa proof at width 256, a
+batch of 2^14 independent vectors per GPU; one "step" = commit all vectors, then open each at a uniform in-domain
+point.  Metric: proofs/s (a proof = one committed-and-opened vector).  Under torchrun every rank runs the same batch
+size (batches shard with no data-path collective: weak scaling) and `value` is the whole-job aggregate over the
+max-over-ranks device time.
 
-Synthetic data is generated ON THE DEVICE by the product itself (CRS points = k_i * G through the library's
-own fixed-base kernel; scalars by rejection sampling with torch); `value` is timed with the inputs resident
-in HBM, `e2e` through the C ABI's host-pointer entry points with pinned host buffers (H2D + D2H inside the
-timed region).  The CPU baseline (`cpu_baseline`, and the whole `--impl reference` arm) is the oracle's
-restatement of the reference's own algorithm (per-term double-and-add, utils.rs:16-19) on the host cores.
+The default run also measures BASELINE's other named metrics and puts them into the same JSON line under `also`
+(msm_2p20 — under torchrun point-range sharded with an all_gather of the partial sums —, commit_w256, kzg_open,
+multiproof_2p12, tree_2p20, and the headline again at the library's default window width c = 16), each with
+`value`, `e2e`, `roofline.frac`, `cpu_baseline` and `checked`.
+
+Every workload CHECKS the outputs of its timed region before its numbers are reported (`checked`): all proofs of the
+last step go through the device verifier, samples are compared byte for byte with the oracle; a mismatch exits
+non-zero.  The oracle is used only there and in the CPU-baseline legs.
+
+Synthetic data is generated ON THE DEVICE by the product itself (CRS points = k_i * G through the library's own
+fixed-base kernel; scalars by rejection sampling with torch); `value` is timed with the inputs resident in HBM, `e2e`
+through the C ABI's host-pointer entry points with pinned host buffers (H2D + D2H inside the timed region).  The CPU
+baseline (`cpu_baseline`, and the whole `--impl reference` arm) is the oracle's restatement of the reference's own
+algorithm (per-term double-and-add, utils.rs:16-19) on the host cores.
 """
 import argparse
 import ctypes
@@ -30,11 +40,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
 MAC32_PER_FQ_MUL = 136          # 8x8 + 8x8 + 8 multiply-accumulates of one Montgomery product
-FQ_MUL_PER_MADD = 10            # XYZZ mixed addition: 8M + 2S
+FQ_MUL_PER_MADD = 10            # XYZZ mixed addition: 8M + 2S (the work model of DESIGN.md section 3, whatever the kernel executes)
 N_WIDTH = 256
-WINDOW_BITS = 16
-WINDOWS = 16
+WORKLOADS = ["ipa", "commit", "msm", "kzg", "multiproof", "tree"]
 
 
 def parse():
@@ -43,11 +53,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="ipa", choices=["ipa", "commit", "msm", "kzg", "multiproof", "tree"])
+    ap.add_argument("--workload", default="ipa", choices=WORKLOADS)
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (default: BASELINE config size)")
     ap.add_argument("--log2n", type=int, default=20, help="msm: log2 of the number of points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--window-bits", type=int, default=0, help="fixed-base window width c of the width-256 key (default 16; up to 20)")
+    ap.add_argument("--no-also", action="store_true", help="headline workload only (no `also` block)")
+    ap.add_argument("--no-check", action="store_true", help="skip the output checks (profiling runs)")
+    ap.add_argument("--window-bits", type=int, default=0, help="fixed-base window width c of the width-256 key (default: largest that fits, up to 20)")
     return ap.parse_args()
 
 
@@ -126,9 +138,6 @@ def make_points_dev(torch, eng, n, gen):
     return out
 
 
-P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
-
-
 def dist_setup(args):
     import torch
     import torch.distributed as dist
@@ -136,9 +145,8 @@ def dist_setup(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # NCCL prints a version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL_DEBUG is left as the caller set it: stdout is diverted to stderr for the lifetime of the process, so NCCL's
+        #  banner cannot end up next to the one JSON line — see emit())
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -190,6 +198,12 @@ def imad_peak(torch, eng):
     return best
 
 
+def _orc():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    return orc
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_cores():
     try:
@@ -198,10 +212,16 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+def _pool_map(fn, items, threads):
+    """the oracle's C entry points release the GIL (ctypes): independent units run on `threads` host threads"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(fn, items))
+
+
 def cpu_ipa_sample(bases_h, nproofs, threads, seed=1):
     """the oracle's commit + low_level_ipa on `nproofs` vectors with `threads` host threads -> (seconds, proofs)"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
+    orc = _orc()
     rng = np.random.default_rng(seed)
     a = orc.rand_fr_buf(rng, nproofs * N_WIDTH).reshape(nproofs, N_WIDTH, 32)
     z = orc.fr_to_buf([int(v) for v in rng.integers(0, N_WIDTH, nproofs)])
@@ -212,8 +232,7 @@ def cpu_ipa_sample(bases_h, nproofs, threads, seed=1):
 
 
 def cpu_commit_sample(bases_h, n, threads, seed=1):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
+    orc = _orc()
     rng = np.random.default_rng(seed)
     a = orc.rand_fr_buf(rng, n * N_WIDTH).reshape(n, N_WIDTH, 32)
     t0 = time.perf_counter()
@@ -223,8 +242,7 @@ def cpu_commit_sample(bases_h, n, threads, seed=1):
 
 def cpu_msm_sample(bases_h, n, threads, seed=1):
     """reference-naive MSM (per-term double-and-add) on the first n points"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
+    orc = _orc()
     rng = np.random.default_rng(seed)
     s = orc.rand_fr_buf(rng, n)
     t0 = time.perf_counter()
@@ -232,13 +250,60 @@ def cpu_msm_sample(bases_h, n, threads, seed=1):
     return time.perf_counter() - t0, n
 
 
+def cpu_kzg_sample(bases_h, n, threads, seed=1):
+    """KZG::commit + KZG::prove_point per vector (benches/kzg.rs:61-75), vectors spread over the host threads"""
+    orc = _orc()
+    rng = np.random.default_rng(seed)
+    a = orc.rand_fr_buf(rng, n * N_WIDTH).reshape(n, N_WIDTH, 32)
+    z = orc.fr_to_buf([int(v) for v in rng.integers(0, N_WIDTH, n)])
+    t0 = time.perf_counter()
+    orc.commit_batch(bases_h[:N_WIDTH], a, nthreads=threads)
+    _pool_map(lambda i: orc.kzg_prove(bases_h[:N_WIDTH], a[i], z[i]), range(n), threads)
+    return time.perf_counter() - t0, n
+
+
+def cpu_multiproof_sample(bases_h, m, threads, seed=1, reps=1):
+    """prove_multiproof over m openings (multiproof.rs:99-176, benches/ipa.rs:111-132); the query commitments are inputs and
+    are not timed.  `reps` independent multiproofs run side by side on the host threads."""
+    orc = _orc()
+    rng = np.random.default_rng(seed)
+    f = orc.rand_fr_buf(rng, m * N_WIDTH).reshape(m, N_WIDTH, 32)
+    z = rng.integers(0, N_WIDTH, m).astype(np.uint64)
+    y = f[np.arange(m), z.astype(np.int64)]
+    C = np.tile(bases_h[:1], (m, 1))   # the transcript only hashes C: any valid points cost the same
+    t0 = time.perf_counter()
+    _pool_map(lambda _i: orc.multiproof_prove("ipa", bases_h, N_WIDTH, f, C, z, y), range(reps), min(threads, reps))
+    return time.perf_counter() - t0, reps
+
+
+def cpu_tree_sample(bases_h, nkeys, threads, seed=1):
+    """VerkleTree insert + commitment (verkle-tree/src/lib.rs:106-137) on independent trees of nkeys keys, one per thread"""
+    orc = _orc()
+    rng = np.random.default_rng(seed)
+    keys = rng.integers(0, 256, (threads, nkeys, 32), dtype=np.uint8)
+    vals = rng.integers(0, 256, (threads, nkeys, 32), dtype=np.uint8)
+    t0 = time.perf_counter()
+    _pool_map(lambda i: orc.tree_commit(bases_h[:N_WIDTH], keys[i], vals[i]), range(threads), threads)
+    return time.perf_counter() - t0, nkeys * threads
+
+
 def reference_bases(n):
     """CRS for the CPU arm when no GPU produced one: the oracle's own walk of points"""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc
+    orc = _orc()
     rng = np.random.default_rng(0x5EED0002)
     k0, k1 = orc.rand_fr(rng, 2)
     return orc.points_walk(k0, k1, n)
+
+
+CPU_ARMS = {
+    # workload: (sample function, units per step as a function of cores, metric, unit, description)
+    "ipa": (cpu_ipa_sample, lambda c: max(c, 8), "ipa_commit_and_prove_proofs_per_s", "proofs/s", "IPA commit + low_level_ipa proof, width 256"),
+    "commit": (cpu_commit_sample, lambda c: 4 * c, "width256_commits_per_s", "commits/s", "width-256 commit"),
+    "msm": (cpu_msm_sample, lambda c: 256 * c, "msm_points_per_s", "points/s", "one MSM (sample of the terms; the reference's per-term double-and-add is linear in n)"),
+    "kzg": (cpu_kzg_sample, lambda c: 4 * c, "kzg_commit_and_open_per_s", "openings/s", "KZG commit + single-point open, width 256"),
+    "multiproof": (None, None, "ipa_multiproofs_per_s", "multiproofs/s", "IPA multiproof over 2^12 openings, width 256"),
+    "tree": (cpu_tree_sample, lambda c: 256, "verkle_tree_commit_keys_per_s", "keys/s", "verkle tree insert + commitment (independent 256-key trees, one per thread)"),
+}
 
 
 def run_reference(args):
@@ -248,24 +313,21 @@ def run_reference(args):
         return
     cores = cpu_cores()
     wl = args.workload
-    if wl == "ipa":
+    fn_s, per_fn, metric, unit, cfg = CPU_ARMS[wl]
+    if wl == "multiproof":
+        m = args.batch or (1 << 12)
         bases = reference_bases(N_WIDTH + 1)
-        per_step = max(cores, 8)
-        fn = lambda: cpu_ipa_sample(bases, per_step, cores)
-        metric, unit, cfg = "ipa_commit_and_prove_proofs_per_s", "proofs/s", "IPA commit + low_level_ipa proof, width 256"
-    elif wl == "commit":
-        bases = reference_bases(N_WIDTH)
-        per_step = 4 * cores
-        fn = lambda: cpu_commit_sample(bases, per_step, cores)
-        metric, unit, cfg = "width256_commits_per_s", "commits/s", "width-256 commit"
-    elif wl == "msm":
+        reps = min(cores, 4)
+        per_step = reps
+        fn = lambda: cpu_multiproof_sample(bases, m, cores, reps=reps)
+    elif wl == "tree":
         per_step = 256 * cores
-        bases = reference_bases(per_step)
-        fn = lambda: cpu_msm_sample(bases, per_step, cores)
-        metric, unit, cfg = "msm_points_per_s", "points/s", f"one MSM of 2^{args.log2n} points (sample of {per_step} terms)"
+        bases = reference_bases(N_WIDTH + 1)
+        fn = lambda: cpu_tree_sample(bases, 256, cores)
     else:
-        emit({"impl": "reference", "unavailable": f"no CPU arm for workload {wl}"})
-        return
+        per_step = per_fn(cores)
+        bases = reference_bases(per_step if wl == "msm" else N_WIDTH + 1)
+        fn = lambda: fn_s(bases, per_step, cores)
     for _ in range(min(args.warmup, 1)):
         fn()
     t0 = time.perf_counter()
@@ -316,30 +378,67 @@ def pick_window_bits(torch, nbases):
     return 16
 
 
-def run_native(args):
-    global WINDOW_BITS, WINDOWS
-    torch, dist, world, rank, local = dist_setup(args)
-    WINDOW_BITS = args.window_bits or pick_window_bits(torch, N_WIDTH + 1)
-    WINDOWS = (256 + WINDOW_BITS - 1) // WINDOW_BITS
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: verkle_kzg_b200 has no CPU path")
-    from verkle_kzg_b200 import Engine, _lib
-    from verkle_kzg_b200._lib import check
-    eng = Engine(local, stream=torch.cuda.current_stream().cuda_stream)
-    L = _lib.lib()
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(0x5EED0002)  # same CRS on every rank
-    wl = args.workload
-    sampler = ClockSampler(local) if rank == 0 else None
-    peak = imad_peak(torch, eng)
-    extra = {}
+class CheckFailed(Exception):
+    pass
+
+
+def _need(cond, what):
+    if not cond:
+        raise CheckFailed(what)
+
+
+class Ctx:
+    """what every workload shares: the process group, the library context, the CRS and its (cached) window key"""
+
+    def __init__(self, args):
+        self.args = args
+        self.torch, self.dist, self.world, self.rank, self.local = dist_setup(args)
+        torch = self.torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: verkle_kzg_b200 has no CPU path")
+        from verkle_kzg_b200 import Engine, _lib
+        self._lib = _lib
+        self.eng = Engine(self.local, stream=torch.cuda.current_stream().cuda_stream)
+        self.L = _lib.lib()
+        self.gen = torch.Generator(device="cuda")
+        self.gen.manual_seed(0x5EED0002)  # same CRS on every rank
+        self.peak = imad_peak(torch, self.eng)
+        self.bases = make_points_dev(torch, self.eng, N_WIDTH + 1, self.gen)       # 256 bases + Q
+        self.bases_h = self.bases.cpu().numpy()
+        self.window_bits = args.window_bits or pick_window_bits(torch, N_WIDTH + 1)
+        self._key, self._key_c, self.key_load_s = None, 0, None
+
+    def key257(self, c):
+        if self._key is not None and self._key_c != c:
+            self._key.free()
+            self._key = None
+        if self._key is None:
+            t = time.perf_counter()
+            self._key = self.eng.load_key_dev(self.bases, N_WIDTH, d_q=self.bases[N_WIDTH:], window_bits=c)
+            self.eng.sync()
+            self.key_load_s = round(time.perf_counter() - t, 2)
+            self._key_c = c
+        return self._key
+
+    def drop_key(self):
+        if self._key is not None:
+            self._key.free()
+            self._key = None
+        self.torch.cuda.empty_cache()
+
+
+def build_workload(ctx, wl, c):
+    """-> dict describing one workload: step / step_e2e closures, the work model, the CPU sample and the output check"""
+    torch, dist, world, rank, eng, L, gen, args = ctx.torch, ctx.dist, ctx.world, ctx.rank, ctx.eng, ctx.L, ctx.gen, ctx.args
+    check = ctx._lib.check
+    W = (256 + c - 1) // c
+    cores = cpu_cores()
+    w = {"wl": wl, "extra": {}, "kernel": "k_fixed_base_msm", "scaling": "weak", "cleanup": lambda: None}
 
     if wl in ("ipa", "commit", "kzg"):
         B = args.batch or (1 << 14)
-        bases = make_points_dev(torch, eng, N_WIDTH + 1, gen)
-        t_key = time.perf_counter()
-        key = eng.load_key_dev(bases, N_WIDTH, d_q=bases[N_WIDTH:] if wl == "ipa" else None, window_bits=WINDOW_BITS)
-        extra["key_load_s"] = round(time.perf_counter() - t_key, 2)
+        key = ctx.key257(c)
+        w["extra"]["key_load_s"] = ctx.key_load_s
         gen.manual_seed(0x5EED1000 + rank)
         a = rand_fr_dev(torch, B * N_WIDTH, gen).reshape(B, N_WIDTH, 32)
         zi = torch.randint(0, N_WIDTH, (B,), device="cuda", generator=gen)
@@ -358,6 +457,7 @@ def run_native(args):
         C_h, L_h, R_h = pinned(torch, (B, 64)), pinned(torch, (B, 8, 64)), pinned(torch, (B, 8, 64))
         tip_h, y_h = pinned(torch, (B, 32)), pinned(torch, (B, 32))
         kid = ctypes.c_uint32(key.id)
+        samples = sorted({0, B // 2 - 1, B // 2, B - 1} & set(range(B)))     # both half-batches of the two-stream split
         if wl == "ipa":
             def step():
                 eng.commit_batch_dev(key, a, N_WIDTH, B, C)
@@ -367,26 +467,52 @@ def run_native(args):
                 # host buffers in, host buffers out: commit + open through the batch entry point (one upload of the rows)
                 check(L.vkzg_ipa_commit_prove_batch(eng._ctx, kid, hp(a_h), hp(z_h), ctypes.c_uint64(B), hp(C_h), hp(L_h), hp(R_h),
                                                     hp(tip_h), hp(y_h)), "commit_prove")
-            madds_per_unit = (N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * WINDOWS          # commit + 8 rounds of two 129-term MSMs
-            launches_timed = 9
+
+            def checker():
+                """every proof of the last timed step through the device verifier (ipa/mod.rs:404-421: prove -> verify), four of
+                them against the oracle byte for byte, and the e2e path's outputs equal to the device-resident path's"""
+                orc = _orc()
+                Cn, Ln, Rn, tn, yn = C.cpu().numpy(), Lr.cpu().numpy(), Rr.cpu().numpy(), tip.cpu().numpy(), y.cpu().numpy()
+                zn, an = z_h.numpy(), a_h.numpy()
+                ok = eng.ipa_verify_batch(key, zn, Cn, Ln, Rn, tn, yn)
+                _need(bool(ok.all()), f"{int((~ok).sum())} of {B} proofs of the timed region fail the device verifier")
+                for i in samples:
+                    eC = orc.commit_batch(ctx.bases_h[:N_WIDTH], an[i:i + 1])[0]
+                    eL, eR, etip, ey = orc.ipa_prove(ctx.bases_h, N_WIDTH, an[i], eC, zn[i])
+                    _need((Cn[i] == eC).all() and (Ln[i] == eL).all() and (Rn[i] == eR).all() and (tn[i] == etip).all()
+                          and (yn[i] == ey).all(), f"proof {i} differs from the oracle")
+                _need((C_h.numpy() == Cn).all() and (L_h.numpy() == Ln).all() and (R_h.numpy() == Rn).all()
+                      and (tip_h.numpy() == tn).all() and (y_h.numpy() == yn).all(), "e2e outputs differ from the device-resident outputs")
+                return {"verified": B, "oracle_samples": len(samples), "e2e_equals_device": True}
+            madds = (N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * W          # commit + 8 rounds of two 129-term MSMs
             h2d = a_h.numel() + z_h.numel()
             d2h = C_h.numel() + L_h.numel() + R_h.numel() + tip_h.numel() + y_h.numel()
-            metric, unit = "ipa_commit_and_prove_proofs_per_s", "proofs/s"
-            cfg = {"workload": "configs[1]: Pedersen/IPA commit + low_level_ipa proof, width 256, batch 2^14 vectors per GPU",
-                   "batch_per_gpu": B, "width": N_WIDTH, "points": "uniform in-domain index per vector"}
-            cpu_fn = cpu_ipa_sample
+            w.update(metric="ipa_commit_and_prove_proofs_per_s", unit="proofs/s",
+                     cfg={"workload": "configs[1]: Pedersen/IPA commit + low_level_ipa proof, width 256, batch 2^14 vectors per GPU",
+                          "batch_per_gpu": B, "width": N_WIDTH, "points": "uniform in-domain index per vector"},
+                     cpu=lambda: cpu_ipa_sample(ctx.bases_h, 4 * cores, cores) + (f"{4 * cores} of the {B} vectors",))
         elif wl == "commit":
             def step():
                 eng.commit_batch_dev(key, a, N_WIDTH, B, C)
 
             def step_e2e():
                 check(L.vkzg_commit_batch(eng._ctx, kid, hp(a_h), ctypes.c_uint32(N_WIDTH), ctypes.c_uint64(B), hp(C_h)), "commit")
-            madds_per_unit = N_WIDTH * WINDOWS
-            launches_timed = 1
+
+            def checker():
+                orc = _orc()
+                Cn, an = C.cpu().numpy(), a_h.numpy()
+                for i in samples:
+                    _need((Cn[i] == orc.commit_batch(ctx.bases_h[:N_WIDTH], an[i:i + 1])[0]).all(), f"commit {i} differs from the oracle")
+                _need((C_h.numpy() == Cn).all(), "e2e outputs differ from the device-resident outputs")
+                # size-independent: commit is linear — commit(a_0 + a_half) = commit(a_0) + commit(a_half)
+                both = eng.fr_vector_op(0, an[0], an[B // 2]).reshape(1, N_WIDTH, 32)
+                _need((eng.commit_batch(key, both)[0] == orc.g1_add(Cn[0], Cn[B // 2])).all(), "commit(a0 + a_half) != commit(a0) + commit(a_half)")
+                return {"oracle_samples": len(samples), "linearity": True, "e2e_equals_device": True}
+            madds = N_WIDTH * W
             h2d, d2h = a_h.numel(), C_h.numel()
-            metric, unit = "width256_commits_per_s", "commits/s"
-            cfg = {"workload": "width-256 Pedersen/KZG commit (M1), batch 2^14 vectors per GPU", "batch_per_gpu": B, "width": N_WIDTH}
-            cpu_fn = cpu_commit_sample
+            w.update(metric="width256_commits_per_s", unit="commits/s",
+                     cfg={"workload": "width-256 Pedersen/KZG commit (M1), batch 2^14 vectors per GPU", "batch_per_gpu": B, "width": N_WIDTH},
+                     cpu=lambda: cpu_commit_sample(ctx.bases_h, 16 * cores, cores) + (f"{16 * cores} of the {B} vectors",))
         else:
             def step():
                 eng.commit_batch_dev(key, a, N_WIDTH, B, C)
@@ -395,23 +521,34 @@ def run_native(args):
             def step_e2e():   # commit + open of the same vectors: one upload of the rows
                 check(L.vkzg_kzg_commit_open_batch(eng._ctx, kid, hp(a_h), ctypes.c_uint32(N_WIDTH), ctypes.c_uint32(0), hp(z_h),
                                                    ctypes.c_uint64(B), hp(C_h), hp(L_h), hp(y_h)), "commit+open")
-            madds_per_unit = 2 * N_WIDTH * WINDOWS
-            launches_timed = 2
+
+            def checker():
+                orc = _orc()
+                Cn, pn, yn, an, zn = C.cpu().numpy(), pf.cpu().numpy(), y.cpu().numpy(), a_h.numpy(), z_h.numpy()
+                for i in samples:
+                    epf, ey, ok = orc.kzg_prove(ctx.bases_h[:N_WIDTH], an[i], zn[i])
+                    _need(ok and (pn[i] == epf).all() and (yn[i] == ey).all(), f"opening {i} differs from the oracle")
+                    _need((Cn[i] == orc.commit_batch(ctx.bases_h[:N_WIDTH], an[i:i + 1])[0]).all(), f"commit {i} differs from the oracle")
+                _need((C_h.numpy() == Cn).all() and (L_h.numpy().reshape(-1)[: B * 64].reshape(B, 64) == pn).all() and (y_h.numpy() == yn).all(),
+                      "e2e outputs differ from the device-resident outputs")
+                return {"oracle_samples": len(samples), "e2e_equals_device": True}
+            madds = 2 * N_WIDTH * W
             h2d, d2h = a_h.numel() + z_h.numel(), 2 * C_h.numel() + y_h.numel()
-            metric, unit = "kzg_commit_and_open_per_s", "openings/s"
-            cfg = {"workload": "configs[0] at batch: KZG commit + single-point open, width 256, batch 2^14 per GPU", "batch_per_gpu": B}
-            cpu_fn = None
-        units_per_step = B
-        bases_h = bases.cpu().numpy()
+            w.update(metric="kzg_commit_and_open_per_s", unit="openings/s",
+                     cfg={"workload": "configs[0] at batch: KZG commit + single-point open, width 256, batch 2^14 per GPU", "batch_per_gpu": B},
+                     cpu=lambda: cpu_kzg_sample(ctx.bases_h, 8 * cores, cores) + (f"{8 * cores} of the {B} vectors",))
+        w.update(step=step, step_e2e=step_e2e, check=checker, madds=madds, units=B, h2d=h2d, d2h=d2h)
+
     elif wl == "msm":
         n = 1 << args.log2n
         per = n // world                                                        # point-range sharding (configs[3])
         gen.manual_seed(0x5EED0004 + rank)
         bases = make_points_dev(torch, eng, per, gen)
         t_key = time.perf_counter()
-        key = eng.load_key_dev(bases, per, kind=_lib.KEY_MSM)
-        extra["key_load_s"] = round(time.perf_counter() - t_key, 2)
-        extra["msm_table_gb"] = round(key.table_bytes / 1e9, 2)
+        key = eng.load_key_dev(bases, per, kind=ctx._lib.KEY_MSM)
+        eng.sync()
+        w["extra"]["key_load_s"] = round(time.perf_counter() - t_key, 2)
+        w["extra"]["msm_table_gb"] = round(key.table_bytes / 1e9, 2)
         s = rand_fr_dev(torch, per, gen)
         part = torch.empty((1, 64), dtype=torch.uint8, device="cuda")
         allp = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
@@ -433,19 +570,42 @@ def run_native(args):
                 dist.all_gather_into_tensor(allp, part)
                 eng.g1_sum_dev(allp, world, out)
                 out_h.copy_(out)
-        madds_per_unit = 16                                                      # MSM keys: c = 16 -> 16 signed digits per scalar
-        launches_timed = 1
-        units_per_step = per
-        h2d, d2h = s_h.numel(), 64
-        metric, unit = "msm_points_per_s", "points/s"
-        cfg = {"workload": f"configs[3]: one KZG-commit MSM of 2^{args.log2n} points, point-range sharded over {world} GPU(s)",
-               "points_per_gpu": per}
-        cpu_fn = cpu_msm_sample
-        bases_h = None
+
+        def checker():
+            """a 5000-point prefix against the oracle's bucket method; e2e == device; under torchrun every rank's combined
+            result equals the group sum of the gathered partial sums recomputed by the oracle"""
+            orc = _orc()
+            k = min(5000, per)
+            pre = torch.empty((1, 64), dtype=torch.uint8, device="cuda")
+            eng.msm_dev(key, s, k, pre)
+            eng.sync()
+            _need((pre.cpu().numpy()[0] == orc.msm(bases[:k].cpu().numpy(), s_h.numpy()[:k], mode="pippenger")).all(),
+                  f"MSM over the first {k} points differs from the oracle")
+            res = {"oracle_prefix_points": k}
+            if world > 1:
+                acc = np.zeros(64, dtype=np.uint8)
+                for p in allp.cpu().numpy():
+                    acc = orc.g1_add(acc, p)
+                _need((out.cpu().numpy()[0] == acc).all() and (out_h.numpy()[0] == acc).all(), "combined MSM != sum of the gathered partial sums")
+                res["combine_checked_ranks"] = world
+            else:
+                _need((out_h.numpy()[0] == part.cpu().numpy()[0]).all(), "e2e output differs from the device-resident output")
+                res["e2e_equals_device"] = True
+            return res
+
+        def cleanup():
+            key.free()
+        nsmp = 128 * cores
+        w.update(step=step, step_e2e=step_e2e, check=checker, cleanup=cleanup, madds=16, units=per, h2d=s_h.numel(), d2h=64,
+                 kernel="k_msm_bucket", scaling="strong" if world > 1 else "weak",
+                 metric="msm_points_per_s", unit="points/s",
+                 cfg={"workload": f"configs[3]: one KZG-commit MSM of 2^{args.log2n} points, point-range sharded over {world} GPU(s)"
+                                  + (", partial sums combined by all_gather + group sum" if world > 1 else ""), "points_per_gpu": per},
+                 cpu=lambda: cpu_msm_sample(bases[:nsmp].cpu().numpy(), nsmp, cores) + (f"{nsmp} of the 2^{args.log2n} terms (naive per-term double-and-add scales linearly)",))
+
     elif wl == "multiproof":
         m = args.batch or (1 << 12)                                             # configs[2]: 2^12 openings aggregated
-        bases = make_points_dev(torch, eng, N_WIDTH + 1, gen)
-        key = eng.load_key_dev(bases, N_WIDTH, d_q=bases[N_WIDTH:], window_bits=WINDOW_BITS)
+        key = ctx.key257(c)
         gen.manual_seed(0x5EED3000 + rank)
         f = rand_fr_dev(torch, m * N_WIDTH, gen).reshape(m, N_WIDTH, 32)
         zi = torch.randint(0, N_WIDTH, (m,), device="cuda", generator=gen)
@@ -468,21 +628,28 @@ def run_native(args):
         def step_e2e():
             check(L.vkzg_multiproof_prove(eng._ctx, kid, ctypes.c_int32(0), hp(f_h), hp(C_h), zp, hp(y_h), ctypes.c_uint64(m), hp(D_h),
                                           hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof")
-        madds_per_unit = (2 * N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * WINDOWS   # D, E commits + the final IPA opening
-        launches_timed = 10
-        units_per_step = 1
-        h2d, d2h = f_h.numel() + m * (64 + 8 + 32), 64 + 2 * 8 * 64 + 64
-        metric, unit = "ipa_multiproofs_per_s", "multiproofs/s"
-        cfg = {"workload": f"configs[2]: IPA multiproof aggregating {m} openings at width 256 (one multiproof per step per GPU; replicas across GPUs)",
-               "openings_per_multiproof": m}
-        cpu_fn = None
-        bases_h = None
+
+        def checker():
+            orc = _orc()
+            got = dict(D=D_h.numpy().copy(), L=L_h.numpy().copy(), R=R_h.numpy().copy(), tip=tip_h.numpy().copy(), y=yo_h.numpy().copy())
+            _need(eng.multiproof_verify_ipa(key, C_h.numpy(), z_h, y_h.numpy(), got), "the multiproof of the timed region fails the device verifier")
+            exp = orc.multiproof_prove("ipa", ctx.bases_h, N_WIDTH, f_h.numpy(), C_h.numpy(), z_h, y_h.numpy())
+            _need(all((got[k] == exp[k]).all() for k in got), "the multiproof differs from the oracle's")
+            return {"verified": 1, "oracle_samples": 1}
+        reps = min(cores, 4)
+        w.update(step=step, step_e2e=step_e2e, check=checker, units=1,
+                 madds=(2 * N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * W,          # D, E commits + the final IPA opening
+                 h2d=f_h.numel() + m * (64 + 8 + 32), d2h=64 + 2 * 8 * 64 + 64,
+                 metric="ipa_multiproofs_per_s", unit="multiproofs/s",
+                 cfg={"workload": f"configs[2]: IPA multiproof aggregating {m} openings at width 256 (one multiproof per step per GPU; replicas across GPUs)",
+                      "openings_per_multiproof": m},
+                 cpu=lambda: cpu_multiproof_sample(ctx.bases_h, m, cores, reps=reps) + (f"{reps} multiproofs of {m} openings side by side",))
+
     elif wl == "tree":
         nkeys = args.batch or (1 << 20)                                         # configs[4]: bulk insert of 2^20 keys
-        from verkle_kzg_b200.tree import build_levels
+        from verkle_kzg_b200.tree import build_levels, NativeVerkleTree
         from verkle_kzg_b200.sharding import split_range
-        bases = make_points_dev(torch, eng, N_WIDTH, gen)
-        key = eng.load_key_dev(bases, N_WIDTH, window_bits=WINDOW_BITS)
+        key = ctx.key257(c)
         rng = np.random.default_rng(0x5EED0005)
         keys_all = rng.integers(0, 256, (nkeys, 32), dtype=np.uint8)
         vals_all = rng.integers(0, 256, (nkeys, 32), dtype=np.uint8)
@@ -495,10 +662,11 @@ def run_native(args):
         total_nodes = sum(counts)
         dev = [dict(rp=torch.from_numpy(lv["row_ptr"].astype(np.int32)).cuda(), sl=torch.from_numpy(lv["slot"].astype(np.int16)).cuda(),
                     ch=torch.from_numpy(lv["child"]).cuda(), li=torch.from_numpy(np.ascontiguousarray(lv["lit"])).cuda(),
-                    n=c, t=len(lv["slot"])) for lv, c in zip(levels, counts)]
+                    n=cn, t=len(lv["slot"])) for lv, cn in zip(levels, counts)]
         nodes = torch.empty((total_nodes, 64), dtype=torch.uint8, device="cuda")
         allp = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
         root = torch.empty((1, 64), dtype=torch.uint8, device="cuda")
+        last = {}
 
         def step():
             off = 0
@@ -510,78 +678,109 @@ def run_native(args):
                 dist.all_gather_into_tensor(allp, nodes[total_nodes - 1:total_nodes])
                 eng.g1_sum_dev(allp, world, root)
 
-        from verkle_kzg_b200.tree import NativeVerkleTree
         kk, vv = keys_all[sel], vals_all[sel]
 
         def step_e2e():
             # configs[4] end to end: bulk insert into the native host tree (libvkzg, Node::insert semantics) + recommit to the root
             t = NativeVerkleTree(32, 256)
             t.insert_many(kk, vv)
-            t.commitment(eng, key)
+            last["root"] = t.commitment(eng, key)
             t.close()
+
+        def checker():
+            """the level-list path (value) and the native host tree (e2e) give the same root; a 300-key tree equals the oracle's"""
+            orc = _orc()
+            _need((nodes[total_nodes - 1].cpu().numpy() == last["root"]).all(), "level-list root != native-tree root")
+            t = NativeVerkleTree(32, 256)
+            t.insert_many(kk[:300], vv[:300])
+            r300 = t.commitment(eng, key)
+            t.close()
+            _need((r300 == orc.tree_commit(ctx.bases_h[:N_WIDTH], kk[:300], vv[:300])).all(), "300-key tree root differs from the oracle")
+            return {"roots_equal": True, "oracle_samples": 1}
         terms = sum(len(lv["slot"]) for lv in levels)
-        madds_per_unit = terms * WINDOWS / max(1, int(sel.sum()))               # upper bound: zero digits are skipped at run time
-        launches_timed = len(levels)
-        units_per_step = int(sel.sum())
         # e2e traffic of vkzg_tree_commit: extensions travel compact (32-byte stem + unit + 32-byte value; the device writes
         # their CSR rows), internal levels as row_ptr + (slot, child) per term; every node commitment is cached back
-        h2d = counts[1] * 65 + sum(4 * (c + 1) + 6 * len(lv["slot"]) for lv, c in zip(levels[2:], counts[2:]))
-        d2h = 64 * sum(counts[1:])
-        metric, unit = "verkle_tree_commit_keys_per_s", "keys/s"
-        cfg = {"workload": f"configs[4]: verkle tree of {nkeys} random 32-byte keys, every node recommitted level by level up to the root",
-               "keys_this_rank": units_per_step, "nodes_per_level": counts, "terms": terms, "host_flatten_seconds_not_timed": round(host_build_s, 1)}
-        cpu_fn = None
-        bases_h = None
+        h2d = counts[1] * 65 + sum(4 * (cn + 1) + 6 * len(lv["slot"]) for lv, cn in zip(levels[2:], counts[2:]))
+        w.update(step=step, step_e2e=step_e2e, check=checker, units=int(sel.sum()), scaling="strong" if world > 1 else "weak",
+                 madds=terms * W / max(1, int(sel.sum())),                      # upper bound: zero digits are skipped at run time
+                 h2d=h2d, d2h=64 * sum(counts[1:]), metric="verkle_tree_commit_keys_per_s", unit="keys/s",
+                 cfg={"workload": f"configs[4]: verkle tree of {nkeys} random 32-byte keys, every node recommitted level by level up to the root",
+                      "keys_this_rank": int(sel.sum()), "nodes_per_level": counts, "terms": terms, "host_flatten_seconds_not_timed": round(host_build_s, 1)},
+                 cpu=lambda: cpu_tree_sample(ctx.bases_h, 256, cores) + (f"{cores} independent trees of 256 keys (node commitments by per-term double-and-add)",))
     else:
         raise SystemExit(f"unknown workload {wl}")
-
-    cfg.update(extra)
     if wl != "msm":
-        cfg["window_bits"] = WINDOW_BITS
-        cfg["window_table_gb"] = round(key.table_bytes / 1e9, 1)
+        w["extra"]["window_bits"] = c
+        w["extra"]["window_table_gb"] = round(ctx._key.table_bytes / 1e9, 1)
+    return w
+
+
+def measure(ctx, wl, c, steps, warmup, sampler=None, cpu=True):
+    """one workload -> its bench line (dict)"""
+    torch, dist, world, rank, eng, args = ctx.torch, ctx.dist, ctx.world, ctx.rank, ctx.eng, ctx.args
+    w = build_workload(ctx, wl, c)
+    step, step_e2e = w["step"], w["step_e2e"]
+    cfg = w["cfg"]
+    cfg.update(w["extra"])
     cfg["l2_policy"] = "tables (GBs) and inputs (>= 128 MB) exceed the 126 MB L2; no flush needed"
     # ---- device-resident timing (the `value`): W warm-up steps, K timed steps
     l0 = eng.launches
-    ms, clocks = timed_steps(torch, dist, world, step, args.steps, args.warmup, sampler)
-    launches = (eng.launches - l0) * args.steps // (args.steps + args.warmup)
+    ms, clocks = timed_steps(torch, dist, world, step, steps, warmup, sampler)
+    launches = (eng.launches - l0) * steps // (steps + warmup)
     # ---- the dominant kernel's own launch durations (roofline): every launch bracketed by a CUDA event pair on its stream.
     #      Taken in a second pass of K steps with the IPA half-batches on ONE stream, so that a bracket times one kernel alone
     #      (in the timed region above the two half-batches interleave on two streams and brackets would overlap).
     eng.set_option(eng.OPT_IPA_TWO_STREAMS, 0)
     step()
     eng.kernel_timing(True)
-    ms_k, _ = timed_steps(torch, dist, world, step, args.steps, 0)
+    ms_k, _ = timed_steps(torch, dist, world, step, steps, 0)
     kn, kms = eng.kernel_timing_read()
     eng.kernel_timing(False)
     eng.set_option(eng.OPT_IPA_TWO_STREAMS, 1)
+    units_per_step = w["units"]
     if world > 1:
         tu = torch.tensor([units_per_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(tu)
         units_all = float(tu.item())
     else:
         units_all = float(units_per_step)
-    total_units = units_all * args.steps
-    value = total_units / (ms * 1e-3)
+    value = units_all * steps / (ms * 1e-3)
+    # ---- one more device-resident step so that the buffers the check reads hold a two-stream result (what was timed)
+    step()
+    torch.cuda.synchronize()
     # ---- end to end through the host-pointer C ABI
     # (2 warm-up steps: the host-pointer path has its own scratch and staging buffers to put into the stream-ordered pool; two
     #  timed repetitions of K/2 steps, the faster one reported: a one-off pool growth or a neighbour's PCIe burst inside a
-    #  2-step window otherwise shows up as a 30 % outlier — seen once in ~20 runs)
-    e2e_steps = max(1, args.steps // 2)
-    ms_e2e = min(timed_steps(torch, dist, world, step_e2e, e2e_steps, 2)[0], timed_steps(torch, dist, world, step_e2e, e2e_steps, 0)[0])
+    #  2-step window otherwise shows up as a 30 % outlier — seen once in ~20 runs; both figures are in the line)
+    e2e_steps = max(1, steps // 2)
+    reps = [timed_steps(torch, dist, world, step_e2e, e2e_steps, 2)[0], timed_steps(torch, dist, world, step_e2e, e2e_steps, 0)[0]]
+    ms_e2e = min(reps)
     e2e_value = units_all * e2e_steps / (ms_e2e * 1e-3)
+    # ---- check what the timed region produced
+    checked = None
+    if not args.no_check:
+        try:
+            checked = w["check"]()
+            checked["ok"] = True
+        except CheckFailed as e:
+            checked = {"ok": False, "error": str(e)}
+    if world > 1 and checked is not None:
+        t = torch.tensor([0.0 if checked["ok"] else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        if t.item() > 0 and checked["ok"]:
+            checked = {"ok": False, "error": "the check failed on another rank"}
+        checked["ranks"] = world
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    macs_per_launch_set = units_per_step * madds_per_unit * FQ_MUL_PER_MADD * MAC32_PER_FQ_MUL
-    achieved = macs_per_launch_set * args.steps / (kms * 1e-3) / 1e12 if kms > 0 else None
+    madds = w["madds"]
+    macs_per_launch_set = units_per_step * madds * FQ_MUL_PER_MADD * MAC32_PER_FQ_MUL
+    achieved = macs_per_launch_set * steps / (kms * 1e-3) / 1e12 if kms > 0 else None
+    peak = ctx.peak
     # The same kernel against the HBM roofline (algorithmic bytes = one 64-byte table point per addition): the gather
     # stream is a few per cent of the measured copy bandwidth, i.e. the kernel is not memory-bound.
     hbm_peak, hbm_src = measured_hbm_peak()
     hbm_view = None
     if kn and kms:
-        gbs = (units_per_step * madds_per_unit * args.steps) * 64.0 / (kms * 1e-3) / 1e9
+        gbs = (units_per_step * madds * steps) * 64.0 / (kms * 1e-3) / 1e9
         hbm_view = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}
     # SURVEY.md section 8d's per-unit figures (8-bit windows, Jacobian 11-mul additions): the work the REFERENCE algorithm
     # would need, not what this kernel executes (wider windows need fewer additions), so its "frac" can exceed 1.
@@ -589,51 +788,92 @@ def run_native(args):
                   "msm": {16: 35.4e3, 18: 31.0e3, 20: 26.1e3}.get(getattr(args, "log2n", 20))}.get(wl)
     survey_acct = None
     if survey_mac and kms:
-        a = units_per_step * survey_mac * args.steps / (kms * 1e-3) / 1e12
+        a = units_per_step * survey_mac * steps / (kms * 1e-3) / 1e12
         survey_acct = {"mac32_per_unit": survey_mac, "achieved": a, "frac": a / peak if peak else None,
                        "note": "reference-algorithm work per unit; > 1 means fewer operations were executed than that algorithm needs"}
     line = {
-        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if wl in ("msm", "tree") else "weak", "vs_baseline": None,
+        "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
         "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": cfg,
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "timing": f"faster of 2 repetitions of {e2e_steps} steps after 2 warm-up steps, CUDA events, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": w["unit"], "h2d_bytes_per_step": int(w["h2d"]), "d2h_bytes_per_step": int(w["d2h"]),
+                "timing": f"faster of 2 repetitions of {e2e_steps} steps after 2 warm-up steps, CUDA events, max over ranks",
+                "repetitions": [units_all * e2e_steps / (t * 1e-3) for t in reps]},
+        "checked": checked,
         "roofline": {
             "bound": "int32",
             "bound_note": "integer multiply pipe (IMAD): 254-bit modular arithmetic is neither hbm- nor tensor-bound; the hbm view of the same kernel is under hbm_view",
-            "kernel": "k_msm_bucket" if wl == "msm" else "k_fixed_base_msm",
+            "kernel": w["kernel"],
             "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": "measured live: dependency-free mad.wide.u32 chains on all SMs (vkzg_probe_imad_dev); MEASURED_PEAKS.json has no integer figure",
-            "work_model": f"{madds_per_unit} mixed additions per unit x {FQ_MUL_PER_MADD} Fq-mul x {MAC32_PER_FQ_MUL} MAC32",
+            "work_model": f"{madds} mixed additions per unit x {FQ_MUL_PER_MADD} Fq-mul x {MAC32_PER_FQ_MUL} MAC32",
             "survey_accounting": survey_acct,
             "kernel_launches_timed": kn, "kernel_ms_total": kms, "kernel_share_of_step": kms / ms_k if ms_k else None,
-            "one_stream_ms_per_step": ms_k / args.steps,
-            # DRAM bytes per launch: 128 B per table addition as ncu measured it on this kernel (dram__bytes_read.sum +
-            # dram__bytes_write.sum of one --set full capture, profiles/r01_ncu_full_summary_final.json: 1.785 GB for a
-            # launch of 13.7 M additions; every 64-byte point is fetched at 128-byte granularity) x additions per launch
-            "traffic": (units_per_step * madds_per_unit * args.steps / kn) * 128.0 if kn else None,
-            "algorithmic_bytes_per_launch": (units_per_step * madds_per_unit * args.steps / kn) * 64.0 if kn else None,
+            "one_stream_ms_per_step": ms_k / steps,
+            # DRAM bytes per launch: NOT measured in this run — 128 B per table addition as ncu measured it on this kernel
+            # (dram__bytes_read.sum + dram__bytes_write.sum of one --set full capture under profiles/: 1.785 GB for a launch of
+            # 13.7 M additions; every 64-byte point is fetched at 128-byte granularity) x additions per launch
+            "traffic": (units_per_step * madds * steps / kn) * 128.0 if kn else None,
+            "traffic_source": "modelled: 128 B per table addition from the ncu --set full capture under profiles/, scaled to this launch size (not measured live)",
+            "algorithmic_bytes_per_launch": (units_per_step * madds * steps / kn) * 64.0 if kn else None,
             "hbm_view": hbm_view,
-            "ncu": "sm__pipe_fmaheavy_cycles_active 85 % (k_fixed_base_msm), 86 % (k_msm_bucket); DRAM read ~10 % of peak (profiles/)",
+            "ncu": "profiles/: sm__pipe_fmaheavy_cycles_active and DRAM bytes of k_fixed_base_msm / k_msm_bucket",
         },
     }
-    if cpu_fn and not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
-        cores = cpu_cores()
-        if wl == "msm":
-            nsmp = 128 * cores
-            bh = make_points_dev(torch, eng, nsmp, gen).cpu().numpy()
-            dt, u = cpu_fn(bh, nsmp, cores)
-            sample = f"{nsmp} of the 2^{args.log2n} terms (naive per-term double-and-add scales linearly)"
-        else:
-            nsmp = 4 * cores if wl == "ipa" else 16 * cores
-            dt, u = cpu_fn(bases_h, nsmp, cores)
-            sample = f"{nsmp} of the {units_per_step} vectors"
-        line["cpu_baseline"] = {"value": u / dt, "unit": unit, "cores": cores, "kind": "port",
+    if cpu and not args.no_cpu_baseline and world == 1 and rank == 0:  # the CPU baseline is reported at N = 1 only
+        dt, u, sample = w["cpu"]()
+        line["cpu_baseline"] = {"value": u / dt, "unit": w["unit"], "cores": cpu_cores(), "kind": "port", "seconds": round(dt, 2),
                                 "sample": sample + "; restated reference algorithm (C++ oracle), not the arkworks binary"}
-    emit(line)
+    w["cleanup"]()
+    del w
+    torch.cuda.empty_cache()
+    return line
+
+
+def condensed(line):
+    """what an `also` entry keeps of a full line"""
+    r = line["roofline"]
+    out = {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": line["steps"],
+           "warmup": line["warmup"], "scaling": line["scaling"], "gpu_launches": line["gpu_launches"],
+           "e2e": {k: line["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+           "roofline": {"kernel": r["kernel"], "frac": r["frac"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"],
+                        "kernel_share_of_step": r["kernel_share_of_step"], "work_model": r["work_model"]},
+           "checked": line["checked"], "config": line["config"]}
+    if "cpu_baseline" in line:
+        out["cpu_baseline"] = line["cpu_baseline"]
+    return out
+
+
+def run_native(args):
+    ctx = Ctx(args)
+    torch, dist, world, rank = ctx.torch, ctx.dist, ctx.world, ctx.rank
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    c = ctx.window_bits
+    line = measure(ctx, args.workload, c, args.steps, args.warmup, sampler)
+    failed = line["checked"] is not None and not line["checked"]["ok"]
+    if args.workload == "ipa" and not args.no_also and not args.batch:
+        also = {}
+        k, wu = min(args.steps, 10), 3
+        plan = [("commit_w256", "commit", c), ("kzg_open", "kzg", c), ("multiproof_2p12", "multiproof", c), ("tree_2p20", "tree", c),
+                (f"msm_2p{args.log2n}", "msm", c)]
+        if c != 16:   # the library's default window width beside the bench's pick
+            plan += [("ipa_c16", "ipa", 16), ("commit_w256_c16", "commit", 16)]
+        for name, wl, cc in plan:
+            try:
+                sub = measure(ctx, wl, cc, k, wu, None, cpu=not name.endswith("_c16"))
+                also[name] = condensed(sub)
+                failed = failed or (sub["checked"] is not None and not sub["checked"]["ok"])
+            except CheckFailed as e:   # (measure() catches these itself; kept for safety)
+                also[name] = {"error": str(e)}
+                failed = True
+        line["also"] = also
+    if rank == 0:
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        sys.stderr.write("bench.py: OUTPUT CHECK FAILED — see `checked` in the JSON line\n")
+        sys.exit(3)
 
 
 _REAL_STDOUT = None

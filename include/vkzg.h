@@ -60,9 +60,16 @@ int32_t vkzg_ctx_sync(vkzg_ctx* ctx);
  * that one half's latency-bound challenge / fold kernels hide under the other half's MSM kernel.
  * VKZG_OPT_TREE_FLATTEN (default 0 = automatic): how vkzg_tree_commit gathers the dirty nodes — 1 = always the sequential
  * bulk pass over the node array, 2 = always the depth-first walk of the dirty paths (automatic: bulk when more than an
- * eighth of the nodes is dirty).  Results are identical; the knob exists for tests and measurements.                */
-enum { VKZG_OPT_IPA_TWO_STREAMS = 1, VKZG_OPT_TREE_FLATTEN = 2 };
+ * eighth of the nodes is dirty).  Results are identical; the knob exists for tests and measurements.
+ * VKZG_OPT_MULTIPROOF_CHECK_Y (default 1): vkzg_multiproof_verify_ipa also requires the proof's evaluation to equal
+ * g2(t) = sum_q r^q y_q / (t - z_q).  The reference computes g2(t) and never compares it (multiproof.rs:201-215), so its
+ * verifier accepts any claimed y_q; 0 reproduces that behaviour exactly.                                                */
+enum { VKZG_OPT_IPA_TWO_STREAMS = 1, VKZG_OPT_TREE_FLATTEN = 2, VKZG_OPT_MULTIPROOF_CHECK_Y = 3 };
 int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value);
+/* Scratch memory comes from a stream-ordered pool private to the context (the device's default pool is not touched); freed
+ * blocks stay cached between calls (VKZG_POOL_KEEP_MB in the environment bounds that) — vkzg_ctx_trim synchronises and
+ * returns them to the driver, vkzg_ctx_destroy does the same.                                                          */
+int32_t vkzg_ctx_trim(vkzg_ctx* ctx);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 uint64_t vkzg_ctx_launches(const vkzg_ctx* ctx);
 
@@ -140,7 +147,9 @@ int32_t vkzg_kzg_commit_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr
 /* ---- I1: IPA::prove_point + low_level_ipa (ipa/mod.rs:137-154, :268-319), batched -------------------- */
 /* a[B][N], points[B], commitments[B].  `prefix` (may be NULL) is the byte state of an in-flight transcript
  * shared by all B proofs (lib.rs:127-133 / multiproof.rs:174), `dst` the transcript's domain label
- * (NULL = "ipa").  Outputs: L[B][log2 N], R[B][log2 N], tip[B], y[B].                                       */
+ * (NULL = "ipa").  The prefix may have any length (like the reference's transcript): beyond 160 bytes its whole
+ * 64-byte blocks are hashed on the host and the device continues from that SHA-256 state.
+ * Outputs: L[B][log2 N], R[B][log2 N], tip[B], y[B].                                                        */
 int32_t vkzg_ipa_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, const vkzg_fr* points,
                              const vkzg_g1_affine* commitments, uint64_t B, const uint8_t* prefix, uint32_t prefix_len,
                              const char* dst, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* y);
@@ -160,6 +169,10 @@ int32_t vkzg_ipa_verify_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* poi
 /* ---- I4: IPA::prove_commitment / verify_commitment_proof (ipa/mod.rs:199-265) ------------------------- */
 int32_t vkzg_ipa_prove_commitment_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* a, const vkzg_g1_affine* commitments,
                                         uint64_t B, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip);
+/* IPA::verify_commitment_proof (ipa/mod.rs:238-265) over B (commitment, proof) pairs of the key's full width:
+ * tip * <G, s> == the folded commitment; ok[B] receives 1 / 0.  The key needs no Q.                              */
+int32_t vkzg_ipa_verify_commitment_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* commitments, uint64_t B,
+                                         const vkzg_g1_affine* L, const vkzg_g1_affine* R, const vkzg_fr* tip, int32_t* ok);
 
 /* ---- P1: VectorCommitmentMultiproof::prove_multiproof (multiproof.rs:99-176) -------------------------- */
 /* scheme: 0 = IPA (key has q), 1 = KZG.  f[m][N], C[m], z[m], y[m].
@@ -206,6 +219,14 @@ int32_t vkzg_tree_insert(vkzg_tree* tree, const uint8_t* keys, const uint8_t* va
 /* 1 = found (value copied to value_out[32]), 0 = absent */
 int32_t vkzg_tree_get(const vkzg_tree* tree, const uint8_t* key, uint8_t* value_out);
 uint64_t vkzg_tree_nodes(const vkzg_tree* tree);
+/* VerkleTree::path_to_stem (verkle-tree/src/lib.rs:131-137, node.rs:101-119): the internal nodes on the way to `stem`
+ * (key_len bytes).  Entry d of the path is the internal node at depth d: its id, the unit stem[d] under which the walk
+ * leaves it (the reference's prefix is stem[0..d+1]) and — when `commitments` is given — its cached commitment (`clean[d]`
+ * = 1) or the identity (`clean[d]` = 0: the node is dirty, call vkzg_tree_commit first).  The walk stops at the first
+ * extension node (not part of the path, like the reference).  VKZG_ERR_RANGE = VerkleError::InvalidPath (an internal node
+ * has no child for the stem).  Arrays hold up to key_len entries; `commitments` / `clean` may be NULL.                  */
+int32_t vkzg_tree_path_to_stem(const vkzg_tree* tree, const uint8_t* stem, uint32_t* path_len, uint32_t* node_ids, uint8_t* units,
+                               vkzg_g1_affine* commitments, uint8_t* clean);
 /* root commitment (Node::gen_commitment, node.rs:212-277) of the current tree; *n_committed = node commitments recomputed by
  * this call (0 when everything was cached).  Dirty extensions travel to the device as 65-byte records and their leaf-side
  * rows are expanded there; all new commitments are cached back on the host.  One tree must not be committed from two

@@ -133,6 +133,7 @@ int hc_transcript_ipa(const uint8_t* prefix, uint32_t prefix_len, const char* ds
                       const uint8_t* L, const uint8_t* R, uint8_t* w_out, uint8_t* x_out) {
     transcript_t t;
     t.len = 0;
+    t.mid_bytes = 0;
     tr_append_raw(t, prefix, prefix_len);
     t.dst_len = (uint32_t)strlen(dst);
     memcpy(t.dst, dst, t.dst_len);

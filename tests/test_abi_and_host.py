@@ -175,6 +175,43 @@ def test_native_tree_insert_get_matches_python_mirror(vk):
         t.insert_single(bytes([1, 2, 9]), bytes(32))
 
 
+def test_native_tree_path_to_stem_matches_python_mirror(vk):
+    """vkzg_tree_path_to_stem against the literal mirror of Node::path_to_stem (node.rs:101-119, lib.rs:131-137): same
+    prefixes and units for present keys, InvalidPath for a stem whose walk meets a missing child"""
+    from verkle_kzg_b200.tree import NativeVerkleTree, VerkleTree
+    rng = np.random.default_rng(23)
+    for key_len, hi in ((32, 256), (4, 3)):
+        keys = rng.integers(0, hi, (400, key_len), dtype=np.uint8)
+        _, first = np.unique(keys[:, : key_len - 1], axis=0, return_index=True)
+        keys = keys[np.sort(first)]
+        vals = rng.integers(0, 256, (len(keys), 32), dtype=np.uint8)
+        keys, vals = _reference_safe(keys, vals, key_len)
+        nt, pt = NativeVerkleTree(key_len, 256), VerkleTree(key_len, 256)
+        nt.insert_many(keys, vals)
+        for k, v in zip(keys, vals):
+            pt.insert_single(k, v)
+        probes = [bytes(k) for k in keys[:60]] + [bytes(rng.integers(0, hi, key_len, dtype=np.uint8)) for _ in range(60)]
+        hits = misses = 0
+        for stem in probes:
+            try:
+                exp = [(pre, unit) for pre, unit, _node in pt.path_to_stem(stem)]
+            except (ValueError, IndexError):
+                exp = None
+            try:
+                got = nt.path_to_stem(stem)
+            except ValueError:
+                got = None
+            if exp is None:
+                assert got is None, stem
+                misses += 1
+            else:
+                assert got is not None and [(pre, unit) for pre, unit, _id, _c in got] == exp, stem
+                assert got[0][2] == 0 and all(c is None for _p, _u, _i, c in got)  # the walk starts at the root; nothing committed yet
+                hits += 1
+        assert hits >= 60 and (misses > 0 or hi == 3)
+        nt.close()
+
+
 def test_split_range():
     from verkle_kzg_b200.sharding import split_range
     for total in (0, 1, 7, 8, 1 << 20, (1 << 14) + 3):

@@ -65,3 +65,51 @@ def test_status_codes(eng):
         k.free()
     with pytest.raises(VkzgError):
         eng.commit_batch(wkey, s)                             # freed key
+
+
+def test_key_load_validation_and_range_checks(eng):
+    """off-curve / non-canonical bases are refused at key load (one of them would corrupt unrelated table rows
+    through the shared inversions); window widths whose entry lists do not fit shared memory are refused at load, not at the
+    first launch; a slice [first, first + n) that wraps around 2^64 is refused; the library works afterwards"""
+    from verkle_kzg_b200 import VkzgError, _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(2)
+    k0, k1 = orc.rand_fr(rng, 2)
+    bases = orc.points_walk(k0, k1, 9)
+    bad = bases.copy()
+    bad[3, 32] ^= 1                                            # y changed: not on the curve
+    with pytest.raises(VkzgError) as e:
+        eng.load_key(bad[:8], window_bits=8)
+    assert e.value.status == -2
+    with pytest.raises(VkzgError):
+        eng.load_key(bad[:8], kind=2, window_bits=8)
+    with pytest.raises(VkzgError):
+        eng.load_key(bases[:8], q=bad[3], window_bits=8)      # the check covers Q
+    noncanon = bases.copy()
+    noncanon[0, :32] = np.frombuffer((orc.P_MOD + 5).to_bytes(32, "little"), dtype=np.uint8)   # x >= p
+    with pytest.raises(VkzgError):
+        eng.load_key(noncanon[:8], window_bits=8)
+    with pytest.raises(VkzgError) as e2:
+        eng.load_key(bases[:8], window_bits=2)                 # 128 windows: the per-warp entry list exceeds shared memory
+    assert e2.value.status == -2
+    k3 = eng.load_key(bases[:8], window_bits=3)                # the narrowest that fits
+    s = orc.rand_fr_buf(rng, 8).reshape(1, 8, 32)
+    assert (eng.commit_batch(k3, s) == orc.commit_batch(bases[:8], s)).all()
+    k3.free()
+    mk = eng.load_key(bases[:8], kind=2, window_bits=8)
+    import torch
+    ds = torch.from_numpy(s[0]).cuda()
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    for first, n in ((2 ** 64 - 1, 2), (9, 0), (4, 5), (2 ** 63, 2 ** 63)):
+        st = L.vkzg_msm_range_dev(eng._ctx, ctypes.c_uint32(mk.id), ctypes.c_uint64(first), ctypes.c_void_p(ds.data_ptr()), ctypes.c_uint64(n),
+                                  ctypes.c_void_p(out.data_ptr()))
+        assert st == -3, (first, n, st)
+    assert L.vkzg_msm_range_dev(eng._ctx, ctypes.c_uint32(mk.id), ctypes.c_uint64(4), ctypes.c_void_p(ds.data_ptr()), ctypes.c_uint64(4),
+                                ctypes.c_void_p(out.data_ptr())) == 0
+    eng.sync()
+    assert (out.cpu().numpy() == orc.msm(bases[4:8], s[0, :4])).all()
+    mk.free()
+    eng.trim()                                                 # cached scratch back to the driver; the context keeps working
+    k8 = eng.load_key(bases[:8], window_bits=8)
+    assert (eng.commit_batch(k8, s) == orc.commit_batch(bases[:8], s)).all()
+    k8.free()

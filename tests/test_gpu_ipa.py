@@ -115,6 +115,63 @@ def test_prove_commitment(eng):
     key.free()
 
 
+def test_verify_commitment_proof_on_the_device(eng):
+    """IPA::verify_commitment_proof (ipa/mod.rs:238-265) on the device: accepts what prove_commitment made (on a key WITHOUT
+    Q too), rejects a tampered tip / L / commitment — the same verdicts as the oracle's verifier"""
+    N = 32
+    rng, bases, key = _setup(eng, N, 83, 12)
+    B = 5
+    a = orc.rand_fr_buf(rng, B * N).reshape(B, N, 32)
+    C = eng.commit_batch(key, a)
+    L, R, tip = eng.ipa_prove_commitment_batch(key, a, C)
+    assert eng.ipa_verify_commitment_batch(key, C, L, R, tip).all()
+    one = orc.fr_to_buf([1])[0]
+    tip2, L2, C2 = tip.copy(), L.copy(), C.copy()
+    tip2[0] = orc.field_op(0, "add", tip[0], one)[0]
+    L2[1, 2] = bases[3]
+    C2[2] = bases[4]
+    assert list(eng.ipa_verify_commitment_batch(key, C, L, R, tip2)) == [False, True, True, True, True]
+    assert list(eng.ipa_verify_commitment_batch(key, C, L2, R, tip)) == [True, False, True, True, True]
+    assert list(eng.ipa_verify_commitment_batch(key, C2, L, R, tip)) == [True, True, False, True, True]
+    assert not orc.ipa_verify_commitment(bases, N, C[0], L[0], R[0], tip2[0])
+    assert not orc.ipa_verify_commitment(bases, N, C2[2], L[2], R[2], tip[2])
+    key.free()
+    noq = eng.load_key(bases[:N], window_bits=12)
+    assert eng.ipa_verify_commitment_batch(noq, C, L, R, tip).all()
+    noq.free()
+    # through the trait mirror
+    from verkle_kzg_b200.vector_commit import IPA, LagrangeBasis
+    up = IPA.setup(eng, bases[:N], q=bases[N], window_bits=12)
+    data = LagrangeBasis.from_vec(a[0])
+    c0 = IPA.commit(up, data)
+    pr = IPA.prove_commitment(up, c0, data)
+    assert IPA.verify_commitment_proof(up, c0, pr)
+    pr["tip"] = tip2[0]
+    assert not IPA.verify_commitment_proof(up, c0, pr)
+    up.free()
+
+
+@pytest.mark.parametrize("plen", [0, 15, 16, 17, 160, 161, 208, 209, 1000, 4099])
+def test_inflight_transcript_of_any_length(eng, plen):
+    """the reference's transcript has no size limit (transcript.rs:34-52): prefixes beyond the 160 inline bytes are
+    pre-hashed block-wise on the host (SHA-256 midstate) — every block-boundary case against the oracle"""
+    N = 4
+    rng, bases, key = _setup(eng, N, 84 + plen, 8)
+    a = orc.rand_fr_buf(rng, 2 * N).reshape(2, N, 32)
+    C = eng.commit_batch(key, a)
+    zb = orc.fr_to_buf([1, N + 3])
+    prefix = bytes(rng.integers(0, 256, plen, dtype=np.uint8))
+    L, R, tip, y = eng.ipa_prove_batch(key, a, zb, C, prefix=prefix, dst="multiproof")
+    for i in range(2):
+        eL, eR, etip, ey = orc.ipa_prove(bases, N, a[i], C[i], zb[i], prefix=prefix, dst="multiproof")
+        assert (L[i] == eL).all() and (R[i] == eR).all() and (tip[i] == etip).all() and (y[i] == ey).all(), (plen, i)
+    assert eng.ipa_verify_batch(key, zb, C, L, R, tip, y, prefix=prefix, dst="multiproof").all()
+    if plen:
+        other = bytes([prefix[0] ^ 1]) + prefix[1:]
+        assert not eng.ipa_verify_batch(key, zb, C, L, R, tip, y, prefix=other, dst="multiproof").any()
+    key.free()
+
+
 def test_barycentric(eng):
     N = 256
     rng, bases, key = _setup(eng, N, 80)

@@ -47,12 +47,25 @@ static int32_t ctx_create(vkzg_ctx** out, int32_t device_id, void* cuda_stream, 
         }
         ctx->own_stream = true;
     }
-    // keep freed scratch memory cached in the stream-ordered pool
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
-        uint64_t thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // scratch memory comes from a pool PRIVATE to this context (the device's default pool and its release threshold are the
+    // host application's — torch, another library — and are left alone).  Freed scratch stays cached in the pool between
+    // calls up to VKZG_POOL_KEEP_MB (environment; default: everything) and goes back to the driver at vkzg_ctx_trim /
+    // vkzg_ctx_destroy.
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device_id;
+    if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return VKZG_ERR_CUDA;
     }
+    uint64_t thr = ~0ull;
+    if (const char* e = getenv("VKZG_POOL_KEEP_MB")) thr = (uint64_t)strtoull(e, nullptr, 10) << 20;
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     *out = ctx;
     return VKZG_OK;
 }
@@ -74,6 +87,13 @@ int32_t vkzg_ctx_destroy(vkzg_ctx* ctx) {
     for (auto& kv : ctx->domains) cudaFree(kv.second.omega);
     for (void* h : ctx->host_stage)
         if (h) cudaFreeHost(h);
+    for (auto& ev : ctx->timing_events) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // every scratch block goes back to the driver
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -87,6 +107,15 @@ int32_t vkzg_ctx_sync(vkzg_ctx* ctx) {
     return VKZG_OK;
 }
 
+int32_t vkzg_ctx_trim(vkzg_ctx* ctx) {
+    VK_TRY(ctx_check(ctx));
+    VK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->aux_stream) VK_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+    if (ctx->copy_stream) VK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    VK_CUDA(cudaMemPoolTrimTo(ctx->pool, 0));
+    return VKZG_OK;
+}
+
 uint64_t vkzg_ctx_launches(const vkzg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value) {
@@ -97,6 +126,7 @@ int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value) {
             if (value < 0 || value > 2) return VKZG_ERR_ARG;
             ctx->tree_flatten = value;
             return VKZG_OK;
+        case VKZG_OPT_MULTIPROOF_CHECK_Y: ctx->multiproof_check_y = value != 0; return VKZG_OK;
         default: return VKZG_ERR_ARG;
     }
 }
@@ -142,6 +172,8 @@ int32_t vkzg_key_load_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_bases, uint32_t
     if (c < 2 || c > 20) return VKZG_ERR_ARG;
     k.c = c;
     k.W = (256 + c - 1) / c;
+    // the fixed-base kernel keeps CHUNK_TERMS * W list entries per warp in shared memory: very narrow windows do not fit
+    if (kind == VKZG_KEY_WINDOW && fixed_base_smem_bytes(k.W) > 200 * 1024) return VKZG_ERR_ARG;
     uint32_t nb = n + (k.has_q ? 1 : 0);
     if (kind == VKZG_KEY_WINDOW) {
         if (((uint64_t)nb * k.W) << (c - 1) >= (1ull << 31)) return VKZG_ERR_RANGE;
@@ -150,9 +182,16 @@ int32_t vkzg_key_load_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_bases, uint32_t
         if ((uint64_t)n * k.W >= (1ull << 31)) return VKZG_ERR_RANGE;
     }
     VK_CUDA(cudaMalloc((void**)&k.bases, (size_t)nb * sizeof(affine_t)));
-    VK_CUDA(cudaMemcpyAsync(k.bases, d_bases, (size_t)n * sizeof(affine_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (d_q) VK_CUDA(cudaMemcpyAsync(k.bases + n, d_q, sizeof(affine_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    int32_t st = kind == VKZG_KEY_WINDOW ? build_window_tables(ctx, k) : build_msm_tables(ctx, k);
+    int32_t st = VKZG_OK;
+    if (cudaMemcpyAsync(k.bases, d_bases, (size_t)n * sizeof(affine_t), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess ||
+        (d_q && cudaMemcpyAsync(k.bases + n, d_q, sizeof(affine_t), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)) {
+        cudaGetLastError();
+        st = VKZG_ERR_CUDA;
+    }
+    // every base must be the identity (0,0) or a canonical point of the curve: one off-curve base (a zero denominator in
+    // the batched table additions) would otherwise corrupt the tables of unrelated rows through the shared inversions
+    if (st == VKZG_OK) st = check_points_on_curve(ctx, k.bases, nb);
+    if (st == VKZG_OK) st = kind == VKZG_KEY_WINDOW ? build_window_tables(ctx, k) : build_msm_tables(ctx, k);
     if (st == VKZG_OK && kind == VKZG_KEY_WINDOW) st = build_domain_tables(ctx, k);
     if (st == VKZG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = VKZG_ERR_CUDA;
     if (st != VKZG_OK) {
@@ -202,7 +241,7 @@ int32_t vkzg_msm_range_dev(vkzg_ctx* ctx, uint32_t key_id, uint64_t first, const
     VK_TRY(ctx_check(ctx));
     Key* k = ctx->key(key_id);
     if (!k || k->kind != VKZG_KEY_MSM || !d_out || (n && !d_scalars)) return VKZG_ERR_ARG;
-    if (first + n > k->n) return VKZG_ERR_RANGE;
+    if (first > k->n || n > k->n - first) return VKZG_ERR_RANGE;  // (no wrap-around in first + n)
     return msm_large(ctx, *k, first, (const fp_t*)d_scalars, n, (affine_t*)d_out);
 }
 int32_t vkzg_msm_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_scalars, uint64_t n, vkzg_g1_affine* d_out) {

@@ -132,16 +132,20 @@ VK_HD void blk_put(uint8_t* blk, uint32_t base, uint32_t pos, uint32_t byte) {
 // local-memory round trips, ~90 cycles per byte for a lone thread — more than the compressions themselves.  Here every
 // 64-byte block is zeroed, filled by a few straight segment copies, and read back as words; b1 / b2 take b0 (and
 // b0 ^ b1) from the state words.
+// `mid` / `mid_bytes` (optional): the SHA-256 state after the first mid_bytes (a multiple of 64, >= z_pad_len) bytes of
+// Z_pad || msg were absorbed elsewhere (a long in-flight transcript is pre-hashed on the host); `msg` then holds the
+// message bytes from that position on.
 __host__ __device__ inline void xmd48_words(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len,
-                                            uint32_t z_pad_len, uint32_t b1[8], uint32_t b2[8]) {
+                                            uint32_t z_pad_len, uint32_t b1[8], uint32_t b2[8], const uint32_t* mid = nullptr,
+                                            uint32_t mid_bytes = 0) {
     const uint32_t IV[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
     // b0 = H(Z_pad || msg || I2OSP(48, 2) || I2OSP(0, 1) || DST || I2OSP(len(DST), 1))
-    const uint32_t m0 = z_pad_len, m1 = m0 + msg_len, d0 = m1 + 3, d1 = d0 + dst_len, total = d1 + 1;
+    const uint32_t m0 = mid_bytes ? mid_bytes : z_pad_len, m1 = m0 + msg_len, d0 = m1 + 3, d1 = d0 + dst_len, total = d1 + 1;
     const uint32_t nblk = (total + 9 + 63) / 64;
     uint32_t b0[8], w[16], bw[16];
     uint8_t* bb = reinterpret_cast<uint8_t*>(bw);
-    for (int i = 0; i < 8; ++i) b0[i] = IV[i];
-    for (uint32_t blk = 0; blk < nblk; ++blk) {
+    for (int i = 0; i < 8; ++i) b0[i] = mid_bytes ? mid[i] : IV[i];
+    for (uint32_t blk = mid_bytes / 64; blk < nblk; ++blk) {
         const uint32_t base = blk * 64;
 #pragma unroll
         for (int i = 0; i < 16; ++i) bw[i] = 0;
@@ -227,9 +231,10 @@ __host__ __device__ inline fp_t fr_from_be48_words(const uint32_t b1[8], const u
     return fp_add<S>(fp_mul_ni<S>(r2, lo), fp_mul_ni<S>(r3, hi));
 }
 
-__host__ __device__ inline fp_t hash_to_fr(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
+__host__ __device__ inline fp_t hash_to_fr(const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len,
+                                           const uint32_t* mid = nullptr, uint32_t mid_bytes = 0) {
     uint32_t b1[8], b2[8];
-    xmd48_words(msg, msg_len, dst, dst_len, ARK04_Z_PAD_LEN, b1, b2);
+    xmd48_words(msg, msg_len, dst, dst_len, ARK04_Z_PAD_LEN, b1, b2, mid, mid_bytes);
     return fr_from_be48_words(b1, b2);
 }
 
@@ -264,9 +269,12 @@ __host__ __device__ inline fp_t fr_from_le32_mod_order(const uint8_t b[32]) {
     return fp_mul_ni<S>(r2, v);  // first operand < r, second any 256-bit value
 }
 
-// Transcript state: at most TR_MAX bytes (prefix <= 160, the IPA opening adds <= 121 before the first
-// clearing digest, every later round holds 100).
+// Transcript state: at most TR_MAX bytes held as bytes (an in-flight prefix of up to TR_PREFIX_INLINE bytes, the IPA
+// opening adds <= 121 before the first clearing digest, every later round holds 100).  A LONGER in-flight prefix — the
+// reference's transcript has no size limit — is pre-hashed on the host: `mid` is the SHA-256 state after the first
+// `mid_bytes` bytes of Z_pad || state, and `state` holds what follows (make_prefix in ipa.cu).
 static const uint32_t TR_MAX = 320;
+static const uint32_t TR_PREFIX_INLINE = 160;
 static const uint32_t TR_DST_MAX = 16;
 
 struct transcript_t {
@@ -274,6 +282,8 @@ struct transcript_t {
     uint32_t len;
     uint8_t dst[TR_DST_MAX];
     uint32_t dst_len;
+    uint32_t mid[8];
+    uint32_t mid_bytes;  // 0: nothing pre-hashed
 };
 
 __host__ __device__ inline void tr_append_raw(transcript_t& t, const uint8_t* p, uint32_t n) {
@@ -301,10 +311,11 @@ __host__ __device__ inline void tr_append_fr(transcript_t& t, const fp_t& x, con
 // digest(label, clear = true)
 __host__ __device__ inline fp_t tr_digest(transcript_t& t, const char* label) {
     tr_append_label(t, label);
-    fp_t res = hash_to_fr(t.state, t.len, t.dst, t.dst_len);
+    fp_t res = hash_to_fr(t.state, t.len, t.dst, t.dst_len, t.mid, t.mid_bytes);
     uint8_t b[32];
     fr_serialize(res, b);
     t.len = 0;
+    t.mid_bytes = 0;
     tr_append_raw(t, b, 32);
     tr_append_label(t, label);
     return res;

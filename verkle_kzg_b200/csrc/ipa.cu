@@ -121,11 +121,21 @@ __global__ void __launch_bounds__(128) k_ipa_begin(IpaState st, uint64_t B, uint
 }
 
 struct TrPrefix {
-    uint8_t bytes[160];
+    uint8_t bytes[TR_PREFIX_INLINE];
     uint32_t len;
     uint8_t dst[TR_DST_MAX];
     uint32_t dst_len;
+    uint32_t mid[8];      // SHA-256 state after the first mid_bytes bytes of Z_pad || prefix (long prefixes, pre-hashed on the host)
+    uint32_t mid_bytes;
 };
+__host__ __device__ inline void tr_begin(transcript_t& t, const TrPrefix& pre) {
+    t.len = 0;
+    tr_append_raw(t, pre.bytes, pre.len);
+    t.dst_len = pre.dst_len;
+    for (uint32_t i = 0; i < pre.dst_len; ++i) t.dst[i] = pre.dst[i];
+    for (int i = 0; i < 8; ++i) t.mid[i] = pre.mid[i];
+    t.mid_bytes = pre.mid_bytes;
+}
 
 // transcript start (ipa/mod.rs:286-292): append C, input point, output point; w = digest("w").
 // mode 1 = prove_commitment (ipa/mod.rs:210-213): append C; digest("x") (result unused).
@@ -134,10 +144,7 @@ __global__ void __launch_bounds__(64) k_ipa_transcript_begin(IpaState st, uint64
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     transcript_t t;
-    t.len = 0;
-    tr_append_raw(t, pre.bytes, pre.len);
-    t.dst_len = pre.dst_len;
-    for (uint32_t i = 0; i < pre.dst_len; ++i) t.dst[i] = pre.dst[i];
+    tr_begin(t, pre);
     affine_t c;
     c.x = fp_load(&C[p].x);
     c.y = fp_load(&C[p].y);
@@ -262,9 +269,30 @@ __global__ void __launch_bounds__(64) k_ipa_challenge(IpaState st, uint64_t B, u
 
 static int32_t make_prefix(TrPrefix& pre, const uint8_t* prefix, uint32_t prefix_len, const char* dst) {
     memset(&pre, 0, sizeof(pre));
-    if (prefix_len > sizeof(pre.bytes) || (prefix_len && !prefix)) return VKZG_ERR_ARG;
-    if (prefix_len) memcpy(pre.bytes, prefix, prefix_len);
-    pre.len = prefix_len;
+    if (prefix_len && !prefix) return VKZG_ERR_ARG;
+    if (prefix_len > sizeof(pre.bytes)) {
+        // the reference's transcript has no size limit (transcript.rs:34-52): absorb the whole 64-byte blocks of
+        // Z_pad || prefix here, the device continues from that SHA-256 state with the < 64 bytes that are left
+        const uint32_t IV[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+        for (int i = 0; i < 8; ++i) pre.mid[i] = IV[i];
+        const uint64_t total = (uint64_t)ARK04_Z_PAD_LEN + prefix_len;
+        const uint64_t nblk = total / 64;
+        uint8_t blk[64];
+        for (uint64_t b = 0; b < nblk; ++b) {
+            for (uint32_t i = 0; i < 64; ++i) {
+                uint64_t pos = b * 64 + i;
+                blk[i] = pos < ARK04_Z_PAD_LEN ? 0 : prefix[pos - ARK04_Z_PAD_LEN];
+            }
+            sha256_compress(pre.mid, blk);
+        }
+        pre.mid_bytes = (uint32_t)(nblk * 64);
+        const uint32_t done = pre.mid_bytes - ARK04_Z_PAD_LEN;  // prefix bytes already absorbed
+        pre.len = prefix_len - done;
+        memcpy(pre.bytes, prefix + done, pre.len);
+    } else {
+        if (prefix_len) memcpy(pre.bytes, prefix, prefix_len);
+        pre.len = prefix_len;
+    }
     const char* d = dst ? dst : "ipa";
     size_t dl = strlen(d);
     if (dl == 0 || dl > TR_DST_MAX) return VKZG_ERR_ARG;
@@ -370,27 +398,30 @@ __global__ void __launch_bounds__(128) k_ipa_verify_scalars(uint64_t B, uint32_t
                                                             const fp_t* __restrict__ points, const fp_t* __restrict__ y,
                                                             const fp_t* __restrict__ tip, const affine_t* __restrict__ L,
                                                             const affine_t* __restrict__ R, const fp_t* __restrict__ b, TrPrefix pre,
+                                                            int mode /* 0: verify_point, 1: verify_commitment_proof (:238-265: no point, no y, no Q) */,
                                                             fp_t* __restrict__ fixed_sc /*[B][N+1]*/, fp_t* __restrict__ var_sc /*[B][1+2 rounds]*/) {
     __shared__ fp_t xs_sh[4][17];  // per warp: x_0 .. x_{rounds-1}, then w
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t p = (uint64_t)blockIdx.x * 4 + warp;
     if (p >= B) return;  // (whole warps leave; only __syncwarp below)
-    fp_t* fs = fixed_sc + p * (N + 1);
+    fp_t* fs = fixed_sc + p * (N + (mode == 0 ? 1 : 0));  // (mode 1: no Q term, N scalars per proof)
     fp_t* vs = var_sc + p * (1 + 2 * rounds);
-    const fp_t yy = fp_load(y + p), tp = fp_load(tip + p);
+    const fp_t yy = mode == 0 ? fp_load(y + p) : fp_zero<S>(), tp = fp_load(tip + p);
     if (lane == 0) {
         transcript_t t;
-        t.len = 0;
-        tr_append_raw(t, pre.bytes, pre.len);
-        t.dst_len = pre.dst_len;
-        for (uint32_t i = 0; i < pre.dst_len; ++i) t.dst[i] = pre.dst[i];
+        tr_begin(t, pre);
         affine_t c;
         c.x = fp_load(&C[p].x);
         c.y = fp_load(&C[p].y);
         tr_append_point(t, c, "C");
-        tr_append_fr(t, fp_load(points + p), "input point");
-        tr_append_fr(t, yy, "output point");
-        xs_sh[warp][16] = tr_digest(t, "w");
+        if (mode == 0) {
+            tr_append_fr(t, fp_load(points + p), "input point");
+            tr_append_fr(t, yy, "output point");
+            xs_sh[warp][16] = tr_digest(t, "w");
+        } else {
+            tr_digest(t, "x");                      // ipa/mod.rs:249: drawn and overwritten by the first round's challenge
+            xs_sh[warp][16] = fp_zero<S>();         // w = 0: the Q term vanishes
+        }
         for (uint32_t r = 0; r < rounds; ++r) {
             affine_t l, rr;
             l.x = fp_load(&L[p * rounds + r].x);
@@ -426,7 +457,7 @@ __global__ void __launch_bounds__(128) k_ipa_verify_scalars(uint64_t B, uint32_t
         const fp_t* bb = b + p * N + (uint64_t)lane * per;
         for (uint32_t i = 0; i < per; ++i) {
             fp_t si = fp_load(blk + i);
-            cb = fp_add<S>(cb, fp_mul_ni<S>(fp_load(bb + i), si));
+            if (mode == 0) cb = fp_add<S>(cb, fp_mul_ni<S>(fp_load(bb + i), si));
             fp_store(blk + i, fp_mul_ni<S>(si, tp));
         }
     }
@@ -442,6 +473,7 @@ __global__ void __launch_bounds__(128) k_ipa_verify_scalars(uint64_t B, uint32_t
     }
     fp_store(vs, suf);  // C
     const fp_t w = xs_sh[warp][16];
+    if (mode != 0) return;
     fp_t qs = fp_sub<S>(fp_mul_ni<S>(fp_mul_ni<S>(w, tp), cb), fp_mul_ni<S>(fp_mul_ni<S>(w, yy), suf));
     fp_store(fs + N, qs);
 }
@@ -497,28 +529,29 @@ __global__ void __launch_bounds__(128) k_ipa_verify_final(uint64_t B, uint32_t p
     ok[p] = eq ? 1 : 0;
 }
 
-int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_points, const affine_t* d_C, uint64_t B, const uint8_t* prefix,
+int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, int mode, const fp_t* d_points, const affine_t* d_C, uint64_t B, const uint8_t* prefix,
                         uint32_t prefix_len, const char* dst, const affine_t* d_L, const affine_t* d_R, const fp_t* d_tip,
                         const fp_t* d_y, int32_t* d_ok) {
     if (B == 0) return VKZG_OK;
     const uint32_t N = k.n;
-    if (N < 2 || (N & (N - 1)) || !k.has_q) return VKZG_ERR_UNSUPPORTED;
+    if (N < 2 || (N & (N - 1)) || (mode == 0 && !k.has_q)) return VKZG_ERR_UNSUPPORTED;
     TrPrefix pre;
     VK_TRY(make_prefix(pre, prefix, prefix_len, dst));
     const uint32_t rounds = k.log2n, per = 1 + 2 * rounds;
     if (rounds > 16) return VKZG_ERR_UNSUPPORTED;
     DevBuf<fp_t> b, fs, vs;
     DevBuf<xyzz_t> F, V;
-    VK_TRY(b.alloc(ctx, B * N));
+    VK_TRY(b.alloc(ctx, mode == 0 ? B * N : 1));
     VK_TRY(fs.alloc(ctx, B * (N + 1)));
     VK_TRY(vs.alloc(ctx, B * per));
     VK_TRY(F.alloc(ctx, B));
     VK_TRY(V.alloc(ctx, B * per));
     cudaStream_t s = ctx->stream;
-    VK_TRY(barycentric_batch(ctx, k, d_points, B, b));
-    k_ipa_verify_scalars<<<ceil_div_u64(B, 4), 128, 0, s>>>(B, N, rounds, d_C, d_points, d_y, d_tip, d_L, d_R, b, pre, fs, vs);
+    if (mode == 0) VK_TRY(barycentric_batch(ctx, k, d_points, B, b));
+    k_ipa_verify_scalars<<<ceil_div_u64(B, 4), 128, 0, s>>>(B, N, rounds, d_C, d_points, d_y, d_tip, d_L, d_R, b, pre, mode, fs, vs);
     VK_TRY(launch_check(ctx));
-    VK_TRY(fixed_base_msm(ctx, k, fs, N + 1, B, 0, 0xffffffffu, F));
+    // (mode 1: the (N+1)-th scalar is zero and a key without Q has no row for it: N terms)
+    VK_TRY(fixed_base_msm(ctx, k, fs, mode == 0 ? N + 1 : N, B, 0, 0xffffffffu, F));
     if (B * per <= (uint64_t)ctx->sm_count * 64)
         k_var_scalar_mul<true><<<ceil_div_u64(B * per * 4, 128), 128, 0, s>>>(B, rounds, d_C, d_L, d_R, vs, V);
     else
@@ -675,7 +708,27 @@ int32_t vkzg_ipa_verify_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* poi
     VK_TRY(upload(ctx, dtip, tip, B));
     VK_TRY(upload(ctx, dy, y, B));
     VK_TRY(dok.alloc(ctx, B));
-    VK_TRY(ipa_verify_core(ctx, *k, dp, dc, B, prefix, prefix_len, dst, dL, dR, dtip, dy, dok));
+    VK_TRY(ipa_verify_core(ctx, *k, 0, dp, dc, B, prefix, prefix_len, dst, dL, dR, dtip, dy, dok));
+    VK_TRY(download(ctx, ok, dok.p, B));
+    return stream_sync(ctx);
+}
+
+int32_t vkzg_ipa_verify_commitment_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* commitments, uint64_t B,
+                                         const vkzg_g1_affine* L, const vkzg_g1_affine* R, const vkzg_fr* tip, int32_t* ok) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
+    if (B && (!commitments || !L || !R || !tip || !ok)) return VKZG_ERR_ARG;
+    uint32_t rounds = k->log2n;
+    DevBuf<fp_t> dtip;
+    DevBuf<affine_t> dc, dL, dR;
+    DevBuf<int32_t> dok;
+    VK_TRY(upload(ctx, dc, commitments, B));
+    VK_TRY(upload(ctx, dL, L, B * rounds));
+    VK_TRY(upload(ctx, dR, R, B * rounds));
+    VK_TRY(upload(ctx, dtip, tip, B));
+    VK_TRY(dok.alloc(ctx, B));
+    VK_TRY(ipa_verify_core(ctx, *k, 1, nullptr, dc, B, nullptr, 0, "ipa", dL, dR, dtip, nullptr, dok));
     VK_TRY(download(ctx, ok, dok.p, B));
     return stream_sync(ctx);
 }

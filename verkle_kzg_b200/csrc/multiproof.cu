@@ -262,6 +262,31 @@ static int32_t fr_mul_elementwise(vkzg_ctx* ctx, const fp_t* a, const fp_t* b, u
 
 static const uint32_t MP_SEG = 32;  // queries per segment of the row sum
 
+
+// The verifier's g2(t) = sum_q (r^q / (t - z_q)) y_q  (multiproof.rs:201-208) against the proof's claimed evaluation.  The
+// reference computes this sum and then never uses it, so its verify_multiproof accepts ANY claimed y_q (they only enter the
+// transcript); here the comparison is made (VKZG_OPT_MULTIPROOF_CHECK_Y, default on): ok &= (g2(t) == y_proof).
+__global__ void __launch_bounds__(256) k_mp_check_y(const fp_t* __restrict__ coef, const fp_t* __restrict__ y, uint64_t m,
+                                                    const fp_t* __restrict__ yproof, int32_t* __restrict__ ok) {
+    __shared__ fp_t part[8];
+    fp_t acc = fp_zero<S>();
+    for (uint64_t q = threadIdx.x; q < m; q += 256) acc = fp_add<S>(acc, fp_mul_ni<S>(fp_load(coef + q), fp_load(y + q)));
+#pragma unroll 1
+    for (int mk = 16; mk > 0; mk >>= 1) {
+        fp_t o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.l[i] = __shfl_xor_sync(0xffffffffu, acc.l[i], mk);
+        acc = fp_add<S>(acc, o);
+    }
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fp_t g2 = part[0];
+        for (int i = 1; i < 8; ++i) g2 = fp_add<S>(g2, part[i]);
+        if (!fp_eq(g2, fp_load(yproof))) ok[0] = 0;
+    }
+}
+
 }  // namespace vk
 
 using namespace vk;
@@ -462,7 +487,15 @@ int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1
     VK_TRY(upload(ctx, dtip, tip, 1));
     VK_TRY(upload(ctx, dy, yproof, 1));
     VK_TRY(dok.alloc(ctx, 1));
-    VK_TRY(ipa_verify_core(ctx, *k, dt, Cdiff, 1, tr.state.data(), (uint32_t)tr.state.size(), "multiproof", dL, dR, dtip, dy, dok));
+    VK_TRY(ipa_verify_core(ctx, *k, 0, dt, Cdiff, 1, tr.state.data(), (uint32_t)tr.state.size(), "multiproof", dL, dR, dtip, dy, dok));
+    if (ctx->multiproof_check_y) {
+        DevBuf<fp_t> dyq;
+        VK_TRY(upload(ctx, dyq, y, m));
+        k_mp_check_y<<<1, 256, 0, s>>>(rpow, dyq, m, dy, dok);
+        VK_TRY(launch_check(ctx));
+        VK_TRY(download(ctx, ok, dok.p, 1));
+        return stream_sync(ctx);
+    }
     VK_TRY(download(ctx, ok, dok.p, 1));
     return stream_sync(ctx);
 }

@@ -266,4 +266,42 @@ int32_t build_domain_tables(vkzg_ctx* ctx, Key& k) {
     return build_domain(ctx, lg, k.n, k.dom);
 }
 
+
+// Key-load validation: every base is the identity (0,0) or a canonical (coordinates < p) point with y^2 = x^3 + 3.
+__global__ void __launch_bounds__(128) k_check_on_curve(const affine_t* __restrict__ pts, uint64_t n, uint32_t* __restrict__ bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p;
+    p.x = fp_load(&pts[i].x);
+    p.y = fp_load(&pts[i].y);
+    if (affine_is_inf(p)) return;
+    uint32_t pl[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pl[k] = Q::p(k);
+    bool ok = !geq8(p.x.l, pl) && !geq8(p.y.l, pl);
+    if (ok) {
+        fp_t three = fp_from_u32<Q>(3);
+        fp_t rhs = fp_add<Q>(fp_mul_ni<Q>(fp_mul_ni<Q>(p.x, p.x), p.x), three);
+        ok = fp_eq(fp_mul_ni<Q>(p.y, p.y), rhs);
+    }
+    if (!ok) atomicAdd(bad, 1u);
+}
+
+int32_t check_points_on_curve(vkzg_ctx* ctx, const affine_t* d_points, uint64_t n) {
+    if (n == 0) return VKZG_OK;
+    DevBuf<uint32_t> bad;
+    VK_TRY(bad.alloc(ctx, 1));
+    VK_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), ctx->stream));
+    k_check_on_curve<<<ceil_div_u64(n, 128), 128, 0, ctx->stream>>>(d_points, n, bad);
+    VK_TRY(launch_check(ctx));
+    uint32_t h = 0;
+    VK_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h) {
+        fprintf(stderr, "[vkzg] key load: %u of %llu bases are not points of the curve\n", h, (unsigned long long)n);
+        return VKZG_ERR_ARG;
+    }
+    return VKZG_OK;
+}
+
 }  // namespace vk

@@ -300,6 +300,33 @@ int32_t vkzg_tree_get(const vkzg_tree* t, const uint8_t* key, uint8_t* value_out
 
 uint64_t vkzg_tree_nodes(const vkzg_tree* t) { return t ? t->nodes.size() : 0; }
 
+// Node::path_to_stem (node.rs:101-119): push (prefix, unit, node) for every internal node that has a child under
+// stem[depth]; an extension ends the walk with Ok, a missing child is VerkleError::InvalidPath.
+int32_t vkzg_tree_path_to_stem(const vkzg_tree* t, const uint8_t* stem, uint32_t* path_len, uint32_t* node_ids, uint8_t* units,
+                               vkzg_g1_affine* commitments, uint8_t* clean) {
+    if (!t || !stem || !path_len || !node_ids || !units) return VKZG_ERR_ARG;
+    uint32_t cur = 0, depth = 0;
+    *path_len = 0;
+    while (t->nodes[cur].internal) {
+        if (depth >= t->key_len) return VKZG_ERR_RANGE;  // (the reference indexes the stem out of bounds here)
+        int32_t c = t->child(cur, stem[depth]);
+        if (c < 0) return VKZG_ERR_RANGE;
+        node_ids[depth] = cur;
+        units[depth] = stem[depth];
+        const bool cl = t->is_clean(cur);
+        if (clean) clean[depth] = cl ? 1 : 0;
+        if (commitments) {
+            if (cl)
+                memcpy(&commitments[depth], &t->commits[cur], sizeof(affine_t));
+            else
+                memset(&commitments[depth], 0, sizeof(affine_t));
+        }
+        *path_len = ++depth;
+        cur = (uint32_t)c;
+    }
+    return VKZG_OK;
+}
+
 // VerkleTree::commitment (lib.rs:127-129): recommit every dirty node, leaves first, return the root commitment.
 // *n_committed (optional) = number of node commitments computed by this call (C1 / C2 helper vectors included).
 int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_affine* root_out, uint64_t* n_committed) {

@@ -72,6 +72,8 @@ struct vkzg_ctx {
     cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
     cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
     bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
+    bool multiproof_check_y = true;      // VKZG_OPT_MULTIPROOF_CHECK_Y
+    cudaMemPool_t pool = nullptr;        // private stream-ordered scratch pool (api.cu: ctx_create)
     int tree_flatten = 0;                // VKZG_OPT_TREE_FLATTEN
     // grow-only pinned host staging areas (vkzg_tree_commit: compact node records up, commitments down); pages stay
     // resident and DMA-able between calls instead of being faulted in and staged by the driver every time
@@ -115,9 +117,10 @@ struct DevBuf {
     int32_t alloc(vkzg_ctx* ctx, size_t count) {
         s = ctx->stream;
         if (count == 0) count = 1;
-        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), s);
+        cudaError_t e = cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), ctx->pool, s);
         if (e != cudaSuccess) {
-            fprintf(stderr, "[vkzg] cudaMallocAsync(%zu bytes) failed: %s\n", count * sizeof(T), cudaGetErrorString(e));
+            fprintf(stderr, "[vkzg] cudaMallocFromPoolAsync(%zu bytes) failed: %s\n", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
             p = nullptr;
             return VKZG_ERR_OOM;
         }
@@ -221,9 +224,13 @@ static inline uint64_t pipeline_chunk(uint64_t B) {
 }
 
 static inline uint32_t ceil_div_u64(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+// dynamic shared memory of one k_fixed_base_msm CTA (commit.cu): per warp a list of CHUNK_TERMS * W entries + 32 counters
+static inline size_t fixed_base_smem_bytes(uint32_t W) { return (size_t)WARPS_PER_CTA * (CHUNK_TERMS * W + 32) * sizeof(uint32_t); }
 
 // ---- internal entry points implemented across the .cu files (all take device pointers) -------------
 int32_t normalize_points(vkzg_ctx* ctx, const xyzz_t* d_in, uint64_t n, affine_t* d_out);
+// VKZG_ERR_ARG unless every point is (0,0) or a canonical point with y^2 = x^3 + 3 (synchronises the stream)
+int32_t check_points_on_curve(vkzg_ctx* ctx, const affine_t* d_points, uint64_t n);
 int32_t build_window_tables(vkzg_ctx* ctx, Key& k);
 int32_t build_msm_tables(vkzg_ctx* ctx, Key& k);
 int32_t build_domain_tables(vkzg_ctx* ctx, Key& k);
@@ -240,7 +247,7 @@ int32_t barycentric_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_points, uin
 int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                        const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,
                        affine_t* d_R, fp_t* d_tip, fp_t* d_y);
-int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_points, const affine_t* d_C, uint64_t B, const uint8_t* prefix,
+int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, int mode, const fp_t* d_points, const affine_t* d_C, uint64_t B, const uint8_t* prefix,
                         uint32_t prefix_len, const char* dst, const affine_t* d_L, const affine_t* d_R, const fp_t* d_tip,
                         const fp_t* d_y, int32_t* d_ok);
 int32_t poly_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points, uint64_t B,

@@ -56,6 +56,10 @@ class Engine:
         except Exception:
             pass
 
+    def trim(self):
+        """return the cached scratch memory of this context's private pool to the driver"""
+        check(self._L.vkzg_ctx_trim(self._ctx), "vkzg_ctx_trim")
+
     def sync(self):
         check(self._L.vkzg_ctx_sync(self._ctx), "vkzg_ctx_sync")
 
@@ -65,6 +69,7 @@ class Engine:
 
     OPT_IPA_TWO_STREAMS = 1   # include/vkzg.h
     OPT_TREE_FLATTEN = 2      # 0 automatic, 1 bulk pass, 2 depth-first walk of the dirty paths
+    OPT_MULTIPROOF_CHECK_Y = 3  # 1 (default): verify_multiproof also checks y_proof == g2(t); 0: the reference's behaviour
 
     def set_option(self, option, value):
         check(self._L.vkzg_ctx_set_option(self._ctx, ctypes.c_int32(option), ctypes.c_int32(value)), "vkzg_ctx_set_option")
@@ -235,6 +240,18 @@ class Engine:
                                                       ctypes.c_uint64(B), hptr(L), hptr(R), hptr(tip)),
               "vkzg_ipa_prove_commitment_batch")
         return L, R, tip
+
+    def ipa_verify_commitment_batch(self, key, commitments, L, R, tip):
+        """IPA::verify_commitment_proof (ipa/mod.rs:238-265), batched -> bool [B]"""
+        commitments = u8(commitments, 64).reshape(-1, 64)
+        B = len(commitments)
+        L = u8(L, 64).reshape(B, key.log2n, 64)
+        R = u8(R, 64).reshape(B, key.log2n, 64)
+        tip = u8(tip, 32).reshape(B, 32)
+        ok = np.zeros(B, dtype=np.int32)
+        check(self._L.vkzg_ipa_verify_commitment_batch(self._ctx, ctypes.c_uint32(key.id), hptr(commitments), ctypes.c_uint64(B),
+                                                       hptr(L), hptr(R), hptr(tip), hptr(ok)), "vkzg_ipa_verify_commitment_batch")
+        return ok.astype(bool)
 
     # ---------------------------------------------------------------- E1 / K1 / K2 / K3
     def evaluate_batch(self, key, f, points, domain_n=0):

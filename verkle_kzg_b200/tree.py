@@ -198,6 +198,20 @@ class VerkleTree:
                 return None
         return node.leaves.get(key[-1]) if node.stem == key else None
 
+    def path_to_stem(self, stem):
+        """VerkleTree::path_to_stem (lib.rs:131-137, node.rs:101-119): [(prefix bytes, unit, internal node)] for every
+        internal node on the way to `stem`; ValueError = VerkleError::InvalidPath"""
+        stem = bytes(stem)
+        path, node = [], self.root
+        while isinstance(node, _Int):
+            depth = len(path)
+            child = node.children.get(stem[depth])
+            if child is None:
+                raise ValueError("InvalidPath")
+            path.append((stem[:depth + 1], stem[depth], node))
+            node = child
+        return path
+
     def levels(self):
         return _flatten(self.root, self.ext_width)
 
@@ -254,6 +268,24 @@ class NativeVerkleTree:
     @property
     def nodes(self):
         return int(self._L.vkzg_tree_nodes(self._t))
+
+    def path_to_stem(self, stem):
+        """vkzg_tree_path_to_stem: [(prefix bytes, unit, node id, cached commitment [64] or None when dirty)];
+        ValueError = VerkleError::InvalidPath"""
+        stem = bytes(stem)
+        assert len(stem) == self.key_len
+        s = np.frombuffer(stem, dtype=np.uint8).copy()
+        n = ctypes.c_uint32(0)
+        ids = np.zeros(self.key_len, dtype=np.uint32)
+        units = np.zeros(self.key_len, dtype=np.uint8)
+        com = np.zeros((self.key_len, 64), dtype=np.uint8)
+        clean = np.zeros(self.key_len, dtype=np.uint8)
+        st = self._L.vkzg_tree_path_to_stem(self._t, _lib.hptr(s), ctypes.byref(n), _lib.hptr(ids), _lib.hptr(units), _lib.hptr(com),
+                                            _lib.hptr(clean))
+        if st == -3:
+            raise ValueError("InvalidPath")
+        _lib.check(st, "vkzg_tree_path_to_stem")
+        return [(stem[:d + 1], int(units[d]), int(ids[d]), com[d].copy() if clean[d] else None) for d in range(n.value)]
 
     def commitment(self, engine, key):
         out = np.zeros(64, dtype=np.uint8)

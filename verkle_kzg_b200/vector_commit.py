@@ -136,6 +136,12 @@ class IPA(_Scheme):
         return dict(l=L[0], r=R[0], tip=tip[0])
 
     @staticmethod
+    def verify_commitment_proof(key, commitment, proof):
+        """IPA::verify_commitment_proof (ipa/mod.rs:238-265)"""
+        ok = key.engine.ipa_verify_commitment_batch(key.key, commitment.reshape(1, 64), proof["l"][None], proof["r"][None], proof["tip"][None])
+        return bool(ok[0])
+
+    @staticmethod
     def prove_multiproof(key, queries):
         """VectorCommitmentMultiproof::prove_multiproof (multiproof.rs:99-176).  queries: list of
         (data: LagrangeBasis, commit [64], z: int, y [32])"""
