@@ -505,7 +505,7 @@ def build_workload(ctx, wl, c):
                     _need((Cn[i] == orc.commit_batch(ctx.bases_h[:N_WIDTH], an[i:i + 1])[0]).all(), f"commit {i} differs from the oracle")
                 _need((C_h.numpy() == Cn).all(), "e2e outputs differ from the device-resident outputs")
                 # size-independent: commit is linear — commit(a_0 + a_half) = commit(a_0) + commit(a_half)
-                both = eng.fr_vector_op(0, an[0], an[B // 2]).reshape(1, N_WIDTH, 32)
+                both = eng.fr_vector_op("add", an[0], an[B // 2]).reshape(1, N_WIDTH, 32)
                 _need((eng.commit_batch(key, both)[0] == orc.g1_add(Cn[0], Cn[B // 2])).all(), "commit(a0 + a_half) != commit(a0) + commit(a_half)")
                 return {"oracle_samples": len(samples), "linearity": True, "e2e_equals_device": True}
             madds = N_WIDTH * W

@@ -61,9 +61,12 @@ int32_t vkzg_ctx_sync(vkzg_ctx* ctx);
  * VKZG_OPT_TREE_FLATTEN (default 0 = automatic): how vkzg_tree_commit gathers the dirty nodes — 1 = always the sequential
  * bulk pass over the node array, 2 = always the depth-first walk of the dirty paths (automatic: bulk when more than an
  * eighth of the nodes is dirty).  Results are identical; the knob exists for tests and measurements.
- * VKZG_OPT_MULTIPROOF_CHECK_Y (default 1): vkzg_multiproof_verify_ipa also requires the proof's evaluation to equal
- * g2(t) = sum_q r^q y_q / (t - z_q).  The reference computes g2(t) and never compares it (multiproof.rs:201-215), so its
- * verifier accepts any claimed y_q; 0 reproduces that behaviour exactly.                                                */
+ * VKZG_OPT_MULTIPROOF_CHECK_Y (default 0; diagnostic): vkzg_multiproof_verify_ipa additionally compares the proof's
+ * evaluation with g2(t) = sum_q r^q y_q / (t - z_q), the sum the reference computes and never uses (multiproof.rs:201-215:
+ * its verifier accepts ANY claimed y_q).  The comparison cannot be the default: the reference's prover divides by
+ * (X - w^z) in g but by (t - z), z an INTEGER, in h (multiproof.rs:155-166, quirk Q4), so (h - g)(t) != g2(t) even for an
+ * honest proof — with the option on, every proof made by the reference's algorithm (and by this library, which is
+ * bit-exact with it) is rejected.  See DESIGN.md section 6.                                                            */
 enum { VKZG_OPT_IPA_TWO_STREAMS = 1, VKZG_OPT_TREE_FLATTEN = 2, VKZG_OPT_MULTIPROOF_CHECK_Y = 3 };
 int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value);
 /* Scratch memory comes from a stream-ordered pool private to the context (the device's default pool is not touched); freed

@@ -265,7 +265,8 @@ static const uint32_t MP_SEG = 32;  // queries per segment of the row sum
 
 // The verifier's g2(t) = sum_q (r^q / (t - z_q)) y_q  (multiproof.rs:201-208) against the proof's claimed evaluation.  The
 // reference computes this sum and then never uses it, so its verify_multiproof accepts ANY claimed y_q (they only enter the
-// transcript); here the comparison is made (VKZG_OPT_MULTIPROOF_CHECK_Y, default on): ok &= (g2(t) == y_proof).
+// transcript).  Diagnostic only (VKZG_OPT_MULTIPROOF_CHECK_Y, default off): the reference's prover mixes w^z (in g) with the
+// integer z (in h, quirk Q4), so (h - g)(t) differs from g2(t) for honest proofs too — the comparison rejects them all.
 __global__ void __launch_bounds__(256) k_mp_check_y(const fp_t* __restrict__ coef, const fp_t* __restrict__ y, uint64_t m,
                                                     const fp_t* __restrict__ yproof, int32_t* __restrict__ ok) {
     __shared__ fp_t part[8];

@@ -72,7 +72,7 @@ struct vkzg_ctx {
     cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
     cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
     bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
-    bool multiproof_check_y = true;      // VKZG_OPT_MULTIPROOF_CHECK_Y
+    bool multiproof_check_y = false;     // VKZG_OPT_MULTIPROOF_CHECK_Y (diagnostic, see include/vkzg.h)
     cudaMemPool_t pool = nullptr;        // private stream-ordered scratch pool (api.cu: ctx_create)
     int tree_flatten = 0;                // VKZG_OPT_TREE_FLATTEN
     // grow-only pinned host staging areas (vkzg_tree_commit: compact node records up, commitments down); pages stay

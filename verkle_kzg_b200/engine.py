@@ -69,7 +69,7 @@ class Engine:
 
     OPT_IPA_TWO_STREAMS = 1   # include/vkzg.h
     OPT_TREE_FLATTEN = 2      # 0 automatic, 1 bulk pass, 2 depth-first walk of the dirty paths
-    OPT_MULTIPROOF_CHECK_Y = 3  # 1 (default): verify_multiproof also checks y_proof == g2(t); 0: the reference's behaviour
+    OPT_MULTIPROOF_CHECK_Y = 3  # diagnostic (default 0): verify_multiproof also compares y_proof with g2(t) — see include/vkzg.h
 
     def set_option(self, option, value):
         check(self._L.vkzg_ctx_set_option(self._ctx, ctypes.c_int32(option), ctypes.c_int32(value)), "vkzg_ctx_set_option")
