@@ -65,6 +65,13 @@ extern "C" {
     pub fn vkzg_tree_commit(ctx: *mut vkzg_ctx, key_id: u32, tree: *mut Opaque, root_out: *mut vkzg_g1_affine, n_committed: *mut u64) -> i32;
     pub fn vkzg_tree_destroy(tree: *mut Opaque) -> i32;
     pub fn vkzg_ctx_sync(ctx: *mut vkzg_ctx) -> i32;
+    pub fn vkzg_ctx_trim(ctx: *mut vkzg_ctx) -> i32;
+    pub fn vkzg_ipa_prove_commitment_batch(ctx: *mut vkzg_ctx, key_id: u32, a: *const vkzg_fr, commitments: *const vkzg_g1_affine, b: u64,
+                                           l: *mut vkzg_g1_affine, r: *mut vkzg_g1_affine, tip: *mut vkzg_fr) -> i32;
+    pub fn vkzg_ipa_verify_commitment_batch(ctx: *mut vkzg_ctx, key_id: u32, commitments: *const vkzg_g1_affine, b: u64,
+                                            l: *const vkzg_g1_affine, r: *const vkzg_g1_affine, tip: *const vkzg_fr, ok: *mut i32) -> i32;
+    pub fn vkzg_tree_path_to_stem(tree: *const Opaque, stem: *const u8, path_len: *mut u32, node_ids: *mut u32, units: *mut u8,
+                                  commitments: *mut vkzg_g1_affine, clean: *mut u8) -> i32;
 }
 
 pub type Opaque = c_void;

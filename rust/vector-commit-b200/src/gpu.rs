@@ -15,7 +15,7 @@ use ark_poly::GeneralEvaluationDomain;
 use sha2::Sha256;
 
 use crate::ffi::*;
-use crate::ipa::{IPAError, IPAProof, IPAUniversalParams};
+use crate::ipa::{IPACommitProof, IPAError, IPAProof, IPAUniversalParams};
 use crate::kzg::{KZGError, KZGKey, KZGProof};
 use crate::lagrange_basis::LagrangeBasis;
 use crate::multiproof::{Multiproof, MultiproofProverQuery, MultiproofVerifierQuery, VectorCommitmentMultiproof};
@@ -134,6 +134,12 @@ impl<const N: usize> VectorCommitment for GpuIpa<N> {
         let c = to_abi(commitment);
         let (mut l, mut r) = (vec![vkzg_g1_affine::default(); rounds], vec![vkzg_g1_affine::default(); rounds]);
         let (mut tip, mut y) = (Fr::zero(), Fr::zero());
+        // the library reads a[B][N]: a shorter evaluation vector (LagrangeBasis::from_vec of < N items over a smaller
+        // domain) must not be handed over as is.  The reference zips a with b and G (utils.rs:17, ipa/mod.rs:281-283), i.e.
+        // it would silently prove a truncated statement; here the width must match the key (IPAError::OutOfCRS otherwise).
+        if data.elements_ref().len() != N {
+            return Err(IPAError::OutOfCRS);
+        }
         let st = unsafe {
             vkzg_ipa_prove_batch(key.gpu.ctx, key.gpu.id, fr_ptr(data.elements_ref()), &point as *const Fr as *const vkzg_fr, &c, 1,
                                  prefix.as_ptr(), prefix.len() as u32, dst.as_ptr(), l.as_mut_ptr(), r.as_mut_ptr(),
@@ -178,8 +184,43 @@ impl<const N: usize> VectorCommitment for GpuIpa<N> {
 }
 
 impl<const N: usize> GpuIpa<N> {
+    /// ipa/mod.rs:199-235 -> vkzg_ipa_prove_commitment_batch (B = 1)
+    pub fn prove_commitment(key: &GpuIpaParams<N>, commitment: &G1Projective, data: &LagrangeBasis<Fr, D>) -> Result<IPACommitProof<G1Projective>, IPAError> {
+        if data.elements_ref().len() != N {
+            return Err(IPAError::OutOfCRS); // (the library reads a[B][N])
+        }
+        let rounds = N.trailing_zeros() as usize;
+        let c = to_abi(commitment);
+        let (mut l, mut r) = (vec![vkzg_g1_affine::default(); rounds], vec![vkzg_g1_affine::default(); rounds]);
+        let mut tip = Fr::zero();
+        let st = unsafe {
+            vkzg_ipa_prove_commitment_batch(key.gpu.ctx, key.gpu.id, fr_ptr(data.elements_ref()), &c, 1, l.as_mut_ptr(), r.as_mut_ptr(),
+                                            &mut tip as *mut Fr as *mut vkzg_fr)
+        };
+        if st != 0 {
+            return Err(IPAError::OutOfDomain);
+        }
+        Ok(IPACommitProof { l: l.iter().map(from_abi).collect(), r: r.iter().map(from_abi).collect(), tip })
+    }
+
+    /// ipa/mod.rs:238-265 -> vkzg_ipa_verify_commitment_batch (B = 1)
+    pub fn verify_commitment_proof(key: &GpuIpaParams<N>, commitment: &G1Projective, proof: &IPACommitProof<G1Projective>) -> bool {
+        if proof.l.len() != N.trailing_zeros() as usize || proof.r.len() != proof.l.len() {
+            return false; // (the reference sizes gens by the proof; the library by the key)
+        }
+        let c = to_abi(commitment);
+        let l: Vec<_> = proof.l.iter().map(to_abi).collect();
+        let r: Vec<_> = proof.r.iter().map(to_abi).collect();
+        let mut ok = 0i32;
+        let st = unsafe {
+            vkzg_ipa_verify_commitment_batch(key.gpu.ctx, key.gpu.id, &c, 1, l.as_ptr(), r.as_ptr(), &proof.tip as *const Fr as *const vkzg_fr, &mut ok)
+        };
+        st == 0 && ok == 1
+    }
+
     /// B commitments in one launch — what `Node::gen_commitment` and bulk callers should use.
     pub fn commit_many(key: &GpuIpaParams<N>, rows: &[Fr], width: usize) -> Vec<G1Projective> {
+        assert!(width > 0 && rows.len() % width == 0, "rows must hold whole vectors");
         let b = rows.len() / width;
         let mut out = vec![vkzg_g1_affine::default(); b];
         let st = unsafe { vkzg_commit_batch(key.gpu.ctx, key.gpu.id, fr_ptr(rows), width as u32, b as u64, out.as_mut_ptr()) };
@@ -199,6 +240,9 @@ impl<const N: usize> VectorCommitmentMultiproof for GpuIpa<N> {
         let mut f: Vec<Fr> = Vec::with_capacity(m * N);
         let (mut c, mut z, mut y) = (Vec::with_capacity(m), Vec::with_capacity(m), Vec::with_capacity(m));
         for q in &qs {
+            if q.data.elements_ref().len() != N {
+                return Err(IPAError::OutOfCRS); // rows are read as f[m][N]
+            }
             f.extend_from_slice(q.data.elements_ref());
             c.push(to_abi(q.commit));
             z.push(q.z as u64);

@@ -192,3 +192,21 @@ def test_large_window_bits_and_sparse_scalars(eng):
     s = np.stack([orc.fr_to_buf(v) for v in vals])
     assert (eng.commit_batch(key, s) == orc.commit_batch(bases, s)).all()
     key.free()
+
+
+def test_group_law_against_public_eip196_vectors(eng):
+    """libvkzg's point addition (vkzg_g1_sum) and scalar multiplication (window table of the vector's own point + commit;
+    MSM key) on public alt_bn128 vectors that no part of this repository produced (EIP-196, go-ethereum "chfast1")"""
+    from test_oracle_primitives import EIP196_ADD, EIP196_MUL, EIP196_2G, eip196_point
+    a, b, s = (eip196_point(p) for p in EIP196_ADD)
+    assert (eng.g1_sum(np.stack([a, b])) == s).all()
+    p, k, r = eip196_point(EIP196_MUL[0]), orc.fr_to_buf([EIP196_MUL[1]]), eip196_point(EIP196_MUL[2])
+    for wb in (8, 13, 16):
+        key = eng.load_key(p[None], window_bits=wb)
+        assert (eng.commit_batch(key, k.reshape(1, 1, 32))[0] == r).all(), wb
+        key.free()
+    mk = eng.load_key(p[None], kind=2, window_bits=8)
+    assert (eng.msm(mk, k) == r).all()
+    mk.free()
+    g = orc.g1_generator()
+    assert (eng.g1_sum(np.stack([g, g])) == eip196_point(EIP196_2G)).all()

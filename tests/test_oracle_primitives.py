@@ -117,3 +117,31 @@ def test_domain_generators():
     w = pyref.group_gen(256)
     assert pow(w, 256, pyref.R_MOD) == 1 and pow(w, 128, pyref.R_MOD) != 1
     assert orc.buf_to_fr(orc.domain_gen(20))[0] == pyref.group_gen(32)
+
+
+# Public alt_bn128 vectors (EIP-196 precompiles 0x06 / 0x07; go-ethereum's bn256Add / bn256ScalarMul test files,
+# case "chfast1") — produced by independent implementations, not by this repository's oracle or Python model.
+EIP196_ADD = (("18b18acfb4c2c30276db5411368e7185b311dd124691610c5d3b74034e093dc9", "063c909c4720840cb5134cb9f59fa749755796819658d32efc0d288198f37266"),
+              ("07c2b7f58a84bd6145f00c9c2bc0bb1a187f20ff2c92963a88019e7c6a014eed", "06614e20c147e940f2d70da3f74c9a17df361706a4485c742bd6788478fa17d7"),
+              ("2243525c5efd4b9c3d3c45ac0ca3fe4dd85e830a4ce6b65fa1eeaee202839703", "301d1d33be6da8e509df21cc35964723180eed7532537db9ae5e7d48f195c915"))
+EIP196_MUL = (("2bd3e6d0f3b142924f5ca7b49ce5b9d54c4703d7ae5648e61d02268b1a0a9fb7", "21611ce0a6af85915e2f1d70300909ce2e49dfad4a4619c8390cae66cefdb204"),
+              0x11138ce750fa15c2,
+              ("070a8d6a982153cae4be29d434e8faef8a47b274a053f5a4ee2a6c9c13c31e5c", "031b8ce914eba3a9ffb989f9cdd5b0f01943074bf4f0f315690ec3cec6981afc"))
+EIP196_2G = ("030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3", "15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4")
+
+
+def eip196_point(xy):
+    return orc.pts_to_buf([(int(xy[0], 16), int(xy[1], 16))])[0]
+
+
+def test_group_law_against_public_eip196_vectors():
+    a, b, s = (eip196_point(p) for p in EIP196_ADD)
+    assert orc.g1_on_curve(a) and orc.g1_on_curve(b)
+    assert (orc.g1_add(a, b) == s).all() and (orc.g1_add(b, a) == s).all()
+    p, k, r = eip196_point(EIP196_MUL[0]), EIP196_MUL[1], eip196_point(EIP196_MUL[2])
+    assert (orc.g1_mul(p, orc.fr_to_buf([k])[0]) == r).all()
+    assert (orc.msm(p[None], orc.fr_to_buf([k]), mode="naive") == r).all()
+    assert (orc.msm(p[None], orc.fr_to_buf([k]), mode="pippenger") == r).all()
+    g = orc.g1_generator()
+    assert (orc.g1_add(g, g) == eip196_point(EIP196_2G)).all()
+    assert (orc.g1_mul(g, orc.fr_to_buf([2])[0]) == eip196_point(EIP196_2G)).all()
