@@ -210,3 +210,34 @@ def test_group_law_against_public_eip196_vectors(eng):
     mk.free()
     g = orc.g1_generator()
     assert (eng.g1_sum(np.stack([g, g])) == eip196_point(EIP196_2G)).all()
+
+
+def test_msm_dev_only_enqueues_and_can_be_captured_in_a_cuda_graph():
+    """vkzg.h: `_dev` calls enqueue on the context's stream and return without synchronising.  vkzg_msm_dev decides between
+    the optimistic single pass and the exact counting sort ON THE DEVICE, so the whole call can be captured in a CUDA graph
+    and replayed on new scalars — uniform ones (optimistic pass) and degenerate ones (fallback) through the SAME graph."""
+    import torch
+    from verkle_kzg_b200 import Engine
+    n = 1 << 13
+    bases = _bases(n, 4242)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        eng = Engine(0, stream=st.cuda_stream)
+        key = eng.load_key(bases, kind=2)
+        rng = np.random.default_rng(77)
+        s1, s2 = orc.rand_fr_buf(rng, n), orc.rand_fr_buf(rng, n)
+        same = np.tile(orc.fr_to_buf([0xabcdef12345])[0], (n, 1))
+        d_s = torch.from_numpy(s1).cuda()
+        d_out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        eng.msm_dev(key, d_s, n, d_out)            # warm-up: scratch buffers enter the pool
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            eng.msm_dev(key, d_s, n, d_out)
+        for s in (s2, same, s1):
+            d_s.copy_(torch.from_numpy(s))
+            g.replay()
+            st.synchronize()
+            assert (d_out.cpu().numpy() == orc.msm(bases, s, mode="pippenger")).all()
+        key.free()
+        eng.close()

@@ -26,10 +26,15 @@ __device__ __forceinline__ affine_t load_affine_ro2(const affine_t* p) {
     return a;
 }
 
+// `gate` (may be null): the kernels of the exact two-pass path run only when the optimistic single pass dropped an
+// entry (*gate != 0), the optimistic bucket pass only when it did not — decided ON THE DEVICE, so that an MSM call only
+// enqueues work (no host round trip, capturable in a CUDA graph).
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_msm_digits(const fp_t* __restrict__ scalars, uint64_t n, uint32_t c, uint32_t W,
                                                     uint32_t key_n, uint64_t first, uint32_t* __restrict__ hist_or_cursor,
-                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries) {
+                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fp_t k = fp_from_mont<S>(fp_load_ro(scalars + i));
@@ -76,7 +81,9 @@ __global__ void __launch_bounds__(256) k_msm_scatter_fixed(const fp_t* __restric
 }
 
 // single-CTA exclusive scan of `n` counts (n <= 2^20), also zeroes the counts for their second life as cursors
-__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets) {
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets,
+                                               const uint32_t* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     __shared__ uint32_t sh[1024];
     uint32_t per = (n + 1023) / 1024;
     uint32_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
@@ -100,10 +107,18 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ counts, ui
     if (threadIdx.x == 1023) offsets[n] = sh[1023];
 }
 
+// fallback taken: the bucket sizes of the optimistic pass become the zeroed histogram of the counting sort
+__global__ void __launch_bounds__(256) k_msm_clear_if(uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restrict__ gate) {
+    if (*gate == 0) return;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = 0;
+}
+
 // P (power of two <= 32) adjacent lanes per bucket
 __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                     const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P, uint32_t cap,
-                                                    xyzz_t* __restrict__ buckets) {
+                                                    xyzz_t* __restrict__ buckets, const uint32_t* __restrict__ gate, uint32_t gate_want) {
+    if (gate && (*gate != 0) != (gate_want != 0)) return;
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = (uint32_t)(t / P), p = (uint32_t)(t % P);
     bool live = b < nb;
@@ -223,49 +238,55 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         p_env = e ? atoi(e) : 0;
     }
     while (P < 32 && avg / (P * 2) >= 48) P *= 2;  // ~64 additions per lane (measured best on B200: P = 8 at n = 2^20)
+    // small slices: one lane per bucket leaves most of the GPU idle (2^16 points: 32 K lanes of ~32 dependent additions on
+    // 75 K thread slots) — split the buckets further until the grid fills about two waves, down to ~6 additions per lane
+    while (P < 32 && (uint64_t)nb * P < (uint64_t)ctx->sm_count * 512 * 2 && avg / (P * 2) >= 6) P *= 2;
     if (p_env == 1 || p_env == 2 || p_env == 4 || p_env == 8 || p_env == 16 || p_env == 32) P = (uint32_t)p_env;
     uint64_t threads = (uint64_t)nb * P;
-    bool done = false;
-    // ---- optimistic single pass (uniform scalars): fixed-capacity bucket lists, no count pass, no scan
+    // ---- optimistic single pass (uniform scalars): fixed-capacity bucket lists, no count pass, no scan.  Entries that do
+    //      not fit are counted in *dropped (device memory); the exact two-pass counting sort below is enqueued behind it and
+    //      its kernels return at once unless *dropped != 0 (skewed scalars) — no host synchronisation either way.
     uint64_t cap64 = avg + avg / 4 + 64;
-    if (n >= (1u << 12) && cap64 * nb < (1ull << 31) && !getenv("VKZG_MSM_TWO_PASS")) {
+    const bool optimistic = n >= (1u << 12) && cap64 * nb < (1ull << 31) && !getenv("VKZG_MSM_TWO_PASS");
+    const uint32_t* gate = nullptr;
+    if (optimistic) {
         const uint32_t cap = (uint32_t)cap64;
+        uint32_t* dropped = counts.p + nb;
         VK_TRY(entries.alloc(ctx, (size_t)cap * nb));
-        k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, counts, entries, counts.p + nb);
+        k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, counts, entries, dropped);
         VK_TRY(launch_check(ctx));
-        uint32_t dropped = 0;
-        VK_CUDA(cudaMemcpyAsync(&dropped, counts.p + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        VK_CUDA(cudaStreamSynchronize(s));
-        if (dropped == 0) {
-            KernelTimer timer(ctx);
-            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, buckets);
-            done = true;
-        } else {
-            VK_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * sizeof(uint32_t), s));
-        }
-        VK_TRY(launch_check(ctx));
-    }
-    if (!done) {
-        // ---- exact two-pass counting sort
-        DevBuf<uint32_t> entries2;
-        VK_TRY(offsets.alloc(ctx, nb + 1));
-        VK_TRY(entries2.alloc(ctx, (size_t)n * k.W));
-        if (n) {
-            k_msm_digits<false><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, nullptr, nullptr);
-            VK_TRY(launch_check(ctx));
-        }
-        k_scan<<<1, 1024, 0, s>>>(counts, nb, offsets);
-        VK_TRY(launch_check(ctx));
-        if (n) {
-            k_msm_digits<true><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, offsets, entries2);
-            VK_TRY(launch_check(ctx));
-        }
         {
             KernelTimer timer(ctx);
-            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets);
+            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, buckets, dropped, 0);
         }
         VK_TRY(launch_check(ctx));
+        gate = dropped;
+        k_msm_clear_if<<<ceil_div_u64(nb, 256), 256, 0, s>>>(counts, nb, gate);
+        VK_TRY(launch_check(ctx));
     }
+    // ---- exact two-pass counting sort (always enqueued; its kernels return at once behind a successful optimistic pass:
+    //      ~10 us of empty launches instead of a device -> host -> device round trip).  Its n * W entry buffer (64 MB per
+    //      2^20 points) comes from the context's pool like everything else.
+    DevBuf<uint32_t> entries2;
+    VK_TRY(offsets.alloc(ctx, nb + 1));
+    VK_TRY(entries2.alloc(ctx, (size_t)n * k.W));
+    if (n) {
+        k_msm_digits<false><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, nullptr, nullptr, gate);
+        VK_TRY(launch_check(ctx));
+    }
+    k_scan<<<1, 1024, 0, s>>>(counts, nb, offsets, gate);
+    VK_TRY(launch_check(ctx));
+    if (n) {
+        k_msm_digits<true><<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, counts, offsets, entries2, gate);
+        VK_TRY(launch_check(ctx));
+    }
+    if (gate) {  // (the optimistic launch above is the timed one)
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets, gate, 1);
+    } else {
+        KernelTimer timer(ctx);
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets, gate, 1);
+    }
+    VK_TRY(launch_check(ctx));
     uint32_t segs = (nb + RED_SEG - 1) / RED_SEG;
     uint32_t rblocks = (segs + RED_THREADS - 1) / RED_THREADS;
     VK_TRY(partial.alloc(ctx, rblocks + 1));
