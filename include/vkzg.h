@@ -245,6 +245,30 @@ int32_t vkzg_kzg_setup_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_powers, uint32
  * base 0 is the generator G                                                                                       */
 int32_t vkzg_kzg_powers(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* tau, uint32_t m, vkzg_g1_affine* out);
 
+/* ---- several GPUs of one box behind the same boundary ------------------------------------------------
+ * A group owns one vkzg_ctx per device and one host thread per device per call; ONE host process (e.g. the Rust caller of
+ * the vector-commit traits) drives the box.  Width-N keys are replicated on every device and batches are cut into
+ * contiguous ranges with no exchange (independent vectors); MSM keys are point-range sharded and the per-device partial
+ * sums (64 bytes each) travel to device 0 over NVLink peer copies and are added there.  Results are byte-identical to the
+ * single-device calls (canonical affine points).  device_ids == NULL: devices 0 .. ngpu-1 (ngpu == 0: every visible device);
+ * an id may repeat (several contexts on one device — what the single-GPU tests use).
+ * (One process per GPU instead — torchrun, NCCL — is verkle_kzg_b200/sharding.py: all_gather + vkzg_g1_sum_dev.)        */
+typedef struct vkzg_mgpu vkzg_mgpu;
+int32_t vkzg_mgpu_create(vkzg_mgpu** out, const int32_t* device_ids, uint32_t ngpu);
+int32_t vkzg_mgpu_destroy(vkzg_mgpu* mg);
+uint32_t vkzg_mgpu_size(const vkzg_mgpu* mg);
+/* the i-th device's context, for the single-device entry points (keys loaded through it are its own) */
+vkzg_ctx* vkzg_mgpu_ctx(vkzg_mgpu* mg, uint32_t i);
+int32_t vkzg_mgpu_key_load(vkzg_mgpu* mg, const vkzg_g1_affine* bases, uint32_t n, const vkzg_g1_affine* q, uint32_t kind,
+                           uint32_t window_bits, uint32_t* key_id);
+int32_t vkzg_mgpu_key_free(vkzg_mgpu* mg, uint32_t key_id);
+/* utils::inner_product as one MSM over all devices (KZG::commit at large n, configs[3]) */
+int32_t vkzg_mgpu_msm(vkzg_mgpu* mg, uint32_t key_id, const vkzg_fr* scalars, uint64_t n, vkzg_g1_affine* out);
+/* vkzg_commit_batch / vkzg_ipa_commit_prove_batch with the batch spread over the devices */
+int32_t vkzg_mgpu_commit_batch(vkzg_mgpu* mg, uint32_t key_id, const vkzg_fr* scalars, uint32_t w, uint64_t B, vkzg_g1_affine* out);
+int32_t vkzg_mgpu_ipa_commit_prove_batch(vkzg_mgpu* mg, uint32_t key_id, const vkzg_fr* a, const vkzg_fr* points, uint64_t B,
+                                         vkzg_g1_affine* commitments, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* y);
+
 /* ---- measurement helpers (tools/, bench.py) ------------------------------------------------------------ */
 /* enable != 0: bracket every launch of the dominant kernel (k_fixed_base_msm for window keys, k_msm_bucket for
  * MSM keys) with a CUDA event pair on the context's stream; calling it again clears the record.            */

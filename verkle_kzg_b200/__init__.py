@@ -7,6 +7,6 @@ verkle node commitment, behind the C ABI of include/vkzg.h (libvkzg.so).
 """
 from . import _lib
 from ._lib import VkzgError, build
-from .engine import Engine
+from .engine import Engine, MultiEngine
 
-__all__ = ["Engine", "VkzgError", "build", "_lib"]
+__all__ = ["Engine", "MultiEngine", "VkzgError", "build", "_lib"]

@@ -395,3 +395,74 @@ class Engine:
     def probe_fq_mul_dev(self, d_x, d_y, n, iters):
         check(self._L.vkzg_probe_fq_mul_dev(self._ctx, dptr(d_x), dptr(d_y), ctypes.c_uint64(n), ctypes.c_uint32(iters)),
               "vkzg_probe_fq_mul_dev")
+
+
+class MultiEngine:
+    """vkzg_mgpu_*: one host process driving several GPUs through the C ABI (include/vkzg.h).  `devices`: list of device ids
+    (an id may repeat), or None for every visible device."""
+
+    def __init__(self, devices=None):
+        self._L = _lib.lib()
+        self._L.vkzg_mgpu_size.restype = ctypes.c_uint32
+        self._mg = ctypes.c_void_p()
+        if devices is None:
+            st = self._L.vkzg_mgpu_create(ctypes.byref(self._mg), None, ctypes.c_uint32(0))
+        else:
+            ids = np.ascontiguousarray(devices, dtype=np.int32)
+            st = self._L.vkzg_mgpu_create(ctypes.byref(self._mg), hptr(ids), ctypes.c_uint32(len(ids)))
+        check(st, "vkzg_mgpu_create")
+
+    @property
+    def size(self):
+        return int(self._L.vkzg_mgpu_size(self._mg))
+
+    def close(self):
+        if self._mg:
+            self._L.vkzg_mgpu_destroy(self._mg)
+            self._mg = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_key(self, bases, q=None, kind=KEY_WINDOW, window_bits=0):
+        bases = u8(bases, 64).reshape(-1, 64)
+        qq = None if q is None else u8(q, 64).reshape(64)
+        kid = ctypes.c_uint32(0)
+        check(self._L.vkzg_mgpu_key_load(self._mg, hptr(bases), ctypes.c_uint32(len(bases)), hptr(qq), ctypes.c_uint32(kind),
+                                         ctypes.c_uint32(window_bits), ctypes.byref(kid)), "vkzg_mgpu_key_load")
+        return kid.value, len(bases)
+
+    def free_key(self, key):
+        check(self._L.vkzg_mgpu_key_free(self._mg, ctypes.c_uint32(key[0])), "vkzg_mgpu_key_free")
+
+    def msm(self, key, scalars):
+        s = u8(scalars, 32).reshape(-1, 32)
+        out = np.zeros(64, dtype=np.uint8)
+        check(self._L.vkzg_mgpu_msm(self._mg, ctypes.c_uint32(key[0]), hptr(s), ctypes.c_uint64(len(s)), hptr(out)), "vkzg_mgpu_msm")
+        return out
+
+    def commit_batch(self, key, scalars):
+        s = u8(scalars, 32)
+        B, w = s.shape[0], s.shape[1]
+        out = np.zeros((B, 64), dtype=np.uint8)
+        check(self._L.vkzg_mgpu_commit_batch(self._mg, ctypes.c_uint32(key[0]), hptr(s), ctypes.c_uint32(w), ctypes.c_uint64(B), hptr(out)),
+              "vkzg_mgpu_commit_batch")
+        return out
+
+    def ipa_commit_prove_batch(self, key, a, points):
+        a = u8(a, 32)
+        B, N = a.shape[0], a.shape[1]
+        assert N == key[1]
+        points = u8(points, 32).reshape(B, 32)
+        lg = _log2(N)
+        C = np.zeros((B, 64), dtype=np.uint8)
+        L = np.zeros((B, lg, 64), dtype=np.uint8)
+        R = np.zeros((B, lg, 64), dtype=np.uint8)
+        tip = np.zeros((B, 32), dtype=np.uint8)
+        y = np.zeros((B, 32), dtype=np.uint8)
+        check(self._L.vkzg_mgpu_ipa_commit_prove_batch(self._mg, ctypes.c_uint32(key[0]), hptr(a), hptr(points), ctypes.c_uint64(B), hptr(C),
+                                                       hptr(L), hptr(R), hptr(tip), hptr(y)), "vkzg_mgpu_ipa_commit_prove_batch")
+        return C, L, R, tip, y
