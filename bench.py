@@ -44,7 +44,7 @@ P_MOD = 218882428718392752222464057452572750886963111572978236626890378946452262
 MAC32_PER_FQ_MUL = 136          # 8x8 + 8x8 + 8 multiply-accumulates of one Montgomery product
 FQ_MUL_PER_MADD = 10            # XYZZ mixed addition: 8M + 2S (the work model of DESIGN.md section 3, whatever the kernel executes)
 N_WIDTH = 256
-WORKLOADS = ["ipa", "commit", "msm", "kzg", "multiproof", "tree"]
+WORKLOADS = ["ipa", "commit", "msm", "kzg", "multiproof", "mpbatch", "tree"]
 
 
 def parse():
@@ -302,6 +302,7 @@ CPU_ARMS = {
     "msm": (cpu_msm_sample, lambda c: 256 * c, "msm_points_per_s", "points/s", "one MSM (sample of the terms; the reference's per-term double-and-add is linear in n)"),
     "kzg": (cpu_kzg_sample, lambda c: 4 * c, "kzg_commit_and_open_per_s", "openings/s", "KZG commit + single-point open, width 256"),
     "multiproof": (None, None, "ipa_multiproofs_per_s", "multiproofs/s", "IPA multiproof over 2^12 openings, width 256"),
+    "mpbatch": (None, None, "ipa_multiproofs_per_s", "multiproofs/s", "IPA multiproof over 2^12 openings, width 256"),
     "tree": (cpu_tree_sample, lambda c: 256, "verkle_tree_commit_keys_per_s", "keys/s", "verkle tree insert + commitment (independent 256-key trees, one per thread)"),
 }
 
@@ -314,12 +315,62 @@ def run_reference(args):
     cores = cpu_cores()
     wl = args.workload
     fn_s, per_fn, metric, unit, cfg = CPU_ARMS[wl]
-    if wl == "multiproof":
-        m = args.batch or (1 << 12)
+    if wl in ("multiproof", "mpbatch"):
+        m = (args.batch or (1 << 12)) if wl == "multiproof" else 1 << 12
         bases = reference_bases(N_WIDTH + 1)
         reps = min(cores, 4)
         per_step = reps
         fn = lambda: cpu_multiproof_sample(bases, m, cores, reps=reps)
+    elif wl == "mpbatch":
+        m = 1 << 12                                                             # configs[2] at a batch: K multiproofs of 2^12 openings in one call
+        K = args.batch or 64
+        key = ctx.key257(c)
+        gen.manual_seed(0x5EED3100 + rank)
+        tot = K * m
+        f = rand_fr_dev(torch, tot * N_WIDTH, gen).reshape(tot, N_WIDTH, 32)
+        zi = torch.randint(0, N_WIDTH, (tot,), device="cuda", generator=gen)
+        Cq = torch.empty((tot, 64), dtype=torch.uint8, device="cuda")
+        eng.commit_batch_dev(key, f, N_WIDTH, tot, Cq)
+        yq = f[torch.arange(tot, device="cuda"), zi].contiguous()
+        f_h = pinned(torch, (tot, N_WIDTH, 32))
+        f_h.copy_(f)
+        C_h, y_h = Cq.cpu().contiguous(), yq.cpu().contiguous()
+        z_h = zi.cpu().numpy().astype(np.uint64)
+        me = np.full(K, m, dtype=np.uint64)
+        D_h, L_h, R_h = pinned(torch, (K, 64)), pinned(torch, (K, 8, 64)), pinned(torch, (K, 8, 64))
+        tip_h, yo_h = pinned(torch, (K, 32)), pinned(torch, (K, 32))
+        kid = ctypes.c_uint32(key.id)
+        zp, mp_ = z_h.ctypes.data_as(ctypes.c_void_p), me.ctypes.data_as(ctypes.c_void_p)
+
+        def step():
+            check(L.vkzg_multiproof_prove_batch_dev(eng._ctx, kid, ctypes.c_int32(0), ctypes.c_void_p(f.data_ptr()), hp(C_h), zp, hp(y_h), mp_,
+                                                    ctypes.c_uint64(K), hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_batch_dev")
+
+        def step_e2e():
+            check(L.vkzg_multiproof_prove_batch(eng._ctx, kid, ctypes.c_int32(0), hp(f_h), hp(C_h), zp, hp(y_h), mp_, ctypes.c_uint64(K),
+                                                hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_batch")
+
+        def checker():
+            """every multiproof of the batch through the device verifier; the first and the last against the oracle"""
+            orc = _orc()
+            Cn, yn, fn = C_h.numpy(), y_h.numpy(), f_h.numpy()
+            for i in range(K):
+                pr = dict(D=D_h.numpy()[i], L=L_h.numpy()[i], R=R_h.numpy()[i], tip=tip_h.numpy()[i], y=yo_h.numpy()[i])
+                sl = slice(i * m, (i + 1) * m)
+                _need(eng.multiproof_verify_ipa(key, Cn[sl], z_h[sl], yn[sl], pr), f"multiproof {i} of the batch fails the device verifier")
+                if i in (0, K - 1):
+                    exp = orc.multiproof_prove("ipa", ctx.bases_h, N_WIDTH, fn[sl], Cn[sl], z_h[sl], yn[sl])
+                    _need(all((pr[k] == exp[k]).all() for k in pr), f"multiproof {i} differs from the oracle's")
+            return {"verified": K, "oracle_samples": min(K, 2)}
+        reps = min(cores, 4)
+        w.update(step=step, step_e2e=step_e2e, check=checker, units=K,
+                 madds=(2 * N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * W,
+                 h2d=f_h.numel() + tot * (64 + 8 + 32), d2h=K * (64 + 2 * 8 * 64 + 64),
+                 metric="ipa_multiproofs_per_s", unit="multiproofs/s",
+                 cfg={"workload": f"configs[2] in bulk: {K} IPA multiproofs of {m} openings each (width 256) per call (vkzg_multiproof_prove_batch)",
+                      "openings_per_multiproof": m, "multiproofs_per_call": K},
+                 cpu=lambda: cpu_multiproof_sample(ctx.bases_h, m, cores, reps=reps) + (f"{reps} multiproofs of {m} openings side by side",))
+
     elif wl == "tree":
         per_step = 256 * cores
         bases = reference_bases(N_WIDTH + 1)
@@ -854,7 +905,8 @@ def run_native(args):
     if args.workload == "ipa" and not args.no_also and not args.batch:
         also = {}
         k, wu = min(args.steps, 10), 3
-        plan = [("commit_w256", "commit", c), ("kzg_open", "kzg", c), ("multiproof_2p12", "multiproof", c), ("tree_2p20", "tree", c),
+        plan = [("commit_w256", "commit", c), ("kzg_open", "kzg", c), ("multiproof_2p12", "multiproof", c), ("multiproof_2p12_x64", "mpbatch", c),
+                ("tree_2p20", "tree", c),
                 (f"msm_2p{args.log2n}", "msm", c)]
         if c != 16:   # the library's default window width beside the bench's pick
             plan += [("ipa_c16", "ipa", 16), ("commit_w256_c16", "commit", 16)]

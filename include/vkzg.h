@@ -188,6 +188,16 @@ int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, co
 int32_t vkzg_multiproof_prove_dev(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* d_f, const vkzg_g1_affine* C,
                                   const uint64_t* z, const vkzg_fr* y, uint64_t m, vkzg_g1_affine* D, vkzg_g1_affine* L,
                                   vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout);
+/* K multiproofs in one call (bulk provers: a block's worth of multiproofs, benches/ipa.rs:111-132 in a loop).  Queries are
+ * concatenated: proof k owns rows / (C, z, y) entries [sum_{j<k} m_each[j], + m_each[k]).  Outputs per proof: D[K],
+ * L[K][log2 N], R[K][log2 N], tip[K], yout[K] (KZG: L[K] = proof points).  The K outer transcripts are hashed by host
+ * threads, D_k / E_k are K-job commits and the K inner openings run as ONE IPA batch — byte-identical to K single calls.  */
+int32_t vkzg_multiproof_prove_batch(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
+                                    const uint64_t* z, const vkzg_fr* y, const uint64_t* m_each, uint64_t K, vkzg_g1_affine* D,
+                                    vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout);
+int32_t vkzg_multiproof_prove_batch_dev(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* d_f, const vkzg_g1_affine* C,
+                                        const uint64_t* z, const vkzg_fr* y, const uint64_t* m_each, uint64_t K, vkzg_g1_affine* D,
+                                        vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout);
 /* ---- P2: verify_multiproof (multiproof.rs:178-215), IPA scheme; *ok = 1/0.  (KZG verification is two
  *      pairings, kzg/mod.rs:165-189, and stays on the host side of the shim.)                            */
 int32_t vkzg_multiproof_verify_ipa(vkzg_ctx* ctx, uint32_t key_id, const vkzg_g1_affine* C, const uint64_t* z,

@@ -93,7 +93,9 @@ int32_t vkzg_ctx_destroy(vkzg_ctx* ctx) {
     }
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (auto st : ctx->side_streams) cudaStreamSynchronize(st);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // every scratch block goes back to the driver
+    for (auto st : ctx->side_streams) cudaStreamDestroy(st);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -112,6 +114,7 @@ int32_t vkzg_ctx_trim(vkzg_ctx* ctx) {
     VK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->aux_stream) VK_CUDA(cudaStreamSynchronize(ctx->aux_stream));
     if (ctx->copy_stream) VK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    for (auto st : ctx->side_streams) VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaMemPoolTrimTo(ctx->pool, 0));
     return VKZG_OK;
 }

@@ -139,12 +139,16 @@ __host__ __device__ inline void tr_begin(transcript_t& t, const TrPrefix& pre) {
 
 // transcript start (ipa/mod.rs:286-292): append C, input point, output point; w = digest("w").
 // mode 1 = prove_commitment (ipa/mod.rs:210-213): append C; digest("x") (result unused).
+// prefix_each (may be null): a different in-flight transcript state per proof, each_len <= TR_PREFIX_INLINE bytes each
+// (batched multiproofs: every inner opening continues its own outer transcript)
 __global__ void __launch_bounds__(64) k_ipa_transcript_begin(IpaState st, uint64_t B, const affine_t* __restrict__ C,
-                                                             const fp_t* __restrict__ points, TrPrefix pre, int mode) {
+                                                             const fp_t* __restrict__ points, TrPrefix pre, int mode,
+                                                             const uint8_t* __restrict__ prefix_each, uint32_t each_len) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     transcript_t t;
     tr_begin(t, pre);
+    if (prefix_each) tr_append_raw(t, prefix_each + p * each_len, each_len);
     affine_t c;
     c.x = fp_load(&C[p].x);
     c.y = fp_load(&C[p].y);
@@ -303,15 +307,17 @@ static int32_t make_prefix(TrPrefix& pre, const uint8_t* prefix, uint32_t prefix
 
 static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                                     const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst,
-                                    affine_t* d_L, affine_t* d_R, fp_t* d_tip, fp_t* d_y);
+                                    affine_t* d_L, affine_t* d_R, fp_t* d_tip, fp_t* d_y, const uint8_t* d_prefix_each, uint32_t each_len);
 
 // Big batches are proven as two half-batches on two streams: the per-round challenge / fold kernels are latency-bound
 // (a thread or a warp per proof, 8 dependent rounds), so one half's hash-and-fold runs under the other half's MSM kernel.
 int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                        const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,
-                       affine_t* d_R, fp_t* d_tip, fp_t* d_y) {
+                       affine_t* d_R, fp_t* d_tip, fp_t* d_y, const uint8_t* d_prefix_each, uint32_t each_len) {
+    if (d_prefix_each && (prefix_len || each_len > TR_PREFIX_INLINE)) return VKZG_ERR_ARG;
     if (!ctx->ipa_two_streams || B < 8192)
-        return ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y);
+        return ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y, d_prefix_each,
+                                    each_len);
     if (!ctx->aux_stream) VK_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     uint32_t rounds = 0;
     while ((1u << rounds) < N) ++rounds;
@@ -324,10 +330,12 @@ int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const 
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->aux_stream;                        // everything the second half enqueues (scratch included) goes to the aux stream
     int32_t st1 = ipa_prove_one_stream(ctx, k, mode, N, d_a + B0 * N, d_points ? d_points + B0 : nullptr, d_C + B0, B1, prefix, prefix_len,
-                                       dst, d_L + B0 * rounds, d_R + B0 * rounds, d_tip + B0, d_y + B0);
+                                       dst, d_L + B0 * rounds, d_R + B0 * rounds, d_tip + B0, d_y + B0,
+                                       d_prefix_each ? d_prefix_each + B0 * each_len : nullptr, each_len);
     cudaEventRecord(join, ctx->stream);
     ctx->stream = main_stream;
-    int32_t st0 = ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B0, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y);
+    int32_t st0 = ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B0, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y, d_prefix_each,
+                                       each_len);
     cudaStreamWaitEvent(ctx->stream, join, 0);
     cudaEventDestroy(fork);
     cudaEventDestroy(join);
@@ -338,7 +346,7 @@ int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const 
 // N = vector length (power of two, <= key size).
 static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                        const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,
-                       affine_t* d_R, fp_t* d_tip, fp_t* d_y) {
+                       affine_t* d_R, fp_t* d_tip, fp_t* d_y, const uint8_t* d_prefix_each, uint32_t each_len) {
     if (B == 0) return VKZG_OK;
     if (N < 2 || (N & (N - 1)) || N > k.n) return VKZG_ERR_UNSUPPORTED;
     const bool with_b = mode == 0;
@@ -367,7 +375,7 @@ static int32_t ipa_prove_one_stream(vkzg_ctx* ctx, const Key& k, int mode, uint3
     uint32_t wblocks = ceil_div_u64(B * 32, 128);
     k_ipa_begin<<<wblocks, 128, 0, s>>>(st, B, N, with_b, d_y);
     VK_TRY(launch_check(ctx));
-    k_ipa_transcript_begin<<<ceil_div_u64(B, 64), 64, 0, s>>>(st, B, d_C, d_points, pre, mode);
+    k_ipa_transcript_begin<<<ceil_div_u64(B, 64), 64, 0, s>>>(st, B, d_C, d_points, pre, mode, d_prefix_each, each_len);
     VK_TRY(launch_check(ctx));
     for (uint32_t r = 0; r < rounds; ++r) {
         uint32_t m = N >> (r + 1);

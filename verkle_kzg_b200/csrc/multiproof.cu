@@ -11,6 +11,9 @@
 // while the rows upload (a single GPU thread would need ~2.5 us per 64-byte block).  Everything that touches
 // the rows — powers of r, the segmented row sums, quotients, h, both commitments and the final opening
 // with its own round challenges — runs on the device.
+#include <atomic>
+#include <thread>
+
 #include "vk_common.cuh"
 #include "warp_util.cuh"
 
@@ -184,6 +187,14 @@ __global__ void k_point_sub(const affine_t* a, const affine_t* b, affine_t* out)
     xyzz_t acc = xyzz_from_affine(*a);
     xyzz_madd(acc, affine_neg(*b));
     *out = xyzz_to_affine(acc);
+}
+// out[i] = a[i] - b[i]
+__global__ void __launch_bounds__(64) k_point_sub_many(const affine_t* a, const affine_t* b, uint64_t n, affine_t* out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz_t acc = xyzz_from_affine(a[i]);
+    xyzz_madd(acc, affine_neg(b[i]));
+    out[i] = xyzz_to_affine(acc);
 }
 
 // variable-base scalar multiplications, thread per point (verify_multiproof's E, multiproof.rs:211)
@@ -421,6 +432,272 @@ static int32_t multiproof_prove_impl(vkzg_ctx* ctx, uint32_t key_id, int32_t sch
     }
     VK_TRY(download(ctx, yout, dyo.p, 1));
     return stream_sync(ctx);
+}
+
+}  // extern "C"
+
+// ---- K multiproofs in one call ------------------------------------------------------------------------------------
+// A multiproof is latency-bound on its own (one inner opening = 8 dependent IPA rounds, two single commits, three serial
+// host transcripts): 2.3 ms for 2^12 openings whatever the GPU does.  With K of them in flight every serial step becomes
+// a batch: the K outer transcripts are hashed by host threads while the rows upload, the row kernels of different proofs
+// run on side streams, D_k / E_k are ONE K-job commit each, and the K inner openings are ONE B = K IPA batch whose proofs
+// continue K different transcripts (per-proof prefixes).  Results are byte-identical to K calls of vkzg_multiproof_prove.
+namespace {
+
+struct MpProof {
+    uint64_t m = 0, off = 0;
+    HostTranscript tr{"multiproof"};
+    fp_t r, t;
+    std::vector<uint32_t> order, grp_z, grp_ptr, seg_ptr;
+    std::vector<fp_t> zf;
+    uint32_t n_groups = 0, n_segs = 0;
+    DevBuf<uint32_t> d_order, d_seg_ptr, d_grp_ptr;
+    DevBuf<fp_t> d_zf, rpow, partial, total, quo, inv, dy;
+};
+
+template <class F>
+void parallel_for_host(uint64_t n, F&& f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    uint64_t nt = std::min<uint64_t>(n, hw ? std::min(hw, 16u) : 4u);
+    if (nt <= 1) {
+        for (uint64_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::atomic<uint64_t> next(0);
+    std::vector<std::thread> th;
+    for (uint64_t t = 0; t < nt; ++t)
+        th.emplace_back([&] {
+            for (uint64_t i; (i = next.fetch_add(1)) < n;) f(i);
+        });
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+static int32_t multiproof_prove_batch_impl(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, bool f_on_device,
+                                           const vkzg_g1_affine* C, const uint64_t* z, const vkzg_fr* y, const uint64_t* m_each, uint64_t K,
+                                           vkzg_g1_affine* D, vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW) return VKZG_ERR_ARG;
+    if (K == 0) return VKZG_OK;
+    if (!f || !C || !z || !y || !m_each || !D || !L || !yout) return VKZG_ERR_ARG;
+    if (scheme != 0 && scheme != 1) return VKZG_ERR_ARG;
+    if (scheme == 0 && (!k->has_q || !R || !tip)) return VKZG_ERR_ARG;
+    const uint32_t N = k->n, rounds = k->log2n;
+    if (N & (N - 1)) return VKZG_ERR_UNSUPPORTED;
+    std::vector<std::unique_ptr<MpProof>> P(K);
+    uint64_t total_m = 0;
+    for (uint64_t i = 0; i < K; ++i) {
+        if (m_each[i] == 0) return VKZG_ERR_ARG;
+        P[i].reset(new MpProof());
+        P[i]->m = m_each[i];
+        P[i]->off = total_m;
+        total_m += m_each[i];
+    }
+    if (total_m >= (1ull << 31)) return VKZG_ERR_RANGE;
+    for (uint64_t q = 0; q < total_m; ++q)
+        if (z[q] >= N) return VKZG_ERR_RANGE;
+    cudaStream_t main_stream = ctx->stream;
+    const size_t n_side = 8;
+    while (ctx->side_streams.size() < n_side) {
+        cudaStream_t st;
+        VK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->side_streams.push_back(st);
+    }
+    // rows to the device first (asynchronous for pinned memory): the host transcripts below overlap the copy
+    DevBuf<fp_t> df_buf;
+    const fp_t* df = (const fp_t*)f;
+    if (!f_on_device) {
+        VK_TRY(upload(ctx, df_buf, f, total_m * N));
+        df = df_buf.p;
+    }
+    // ---- phase 1 (host threads): outer transcripts -> r_k, queries grouped by z (multiproof.rs:108-128)
+    parallel_for_host(K, [&](uint64_t i) {
+        MpProof& p = *P[i];
+        const affine_t* Cq = (const affine_t*)C + p.off;
+        const uint64_t* zq = z + p.off;
+        const fp_t* yq = (const fp_t*)y + p.off;
+        p.tr.state.reserve(p.m * 75 + 64);
+        for (uint64_t q = 0; q < p.m; ++q) {
+            p.tr.append_point(Cq[q], "C");
+            p.tr.append_u64(zq[q], "z");
+            p.tr.append_fr(yq[q], "y");
+        }
+        p.r = p.tr.digest("r");
+        std::vector<uint32_t> cnt(N + 1, 0);
+        p.order.resize(p.m);
+        p.grp_ptr.assign(1, 0);
+        p.seg_ptr.assign(1, 0);
+        for (uint64_t q = 0; q < p.m; ++q) cnt[zq[q] + 1]++;
+        for (uint32_t j = 0; j < N; ++j) cnt[j + 1] += cnt[j];
+        {
+            std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+            for (uint64_t q = 0; q < p.m; ++q) p.order[cur[zq[q]]++] = (uint32_t)q;
+        }
+        for (uint32_t zz = 0; zz < N; ++zz) {
+            uint32_t lo = cnt[zz], hi = cnt[zz + 1];
+            if (lo == hi) continue;
+            p.grp_z.push_back(zz);
+            for (uint32_t a = lo; a < hi; a += MP_SEG) p.seg_ptr.push_back(std::min(hi, a + MP_SEG));
+            p.grp_ptr.push_back((uint32_t)p.seg_ptr.size() - 1);
+        }
+        p.n_groups = (uint32_t)p.grp_z.size();
+        p.n_segs = (uint32_t)p.seg_ptr.size() - 1;
+        p.zf.resize(p.n_groups);
+        for (uint32_t g = 0; g < p.n_groups; ++g) p.zf[g] = fp_from_u32<S>(p.grp_z[g]);
+    });
+    // ---- shared buffers (main stream), then fork
+    DevBuf<fp_t> g_all, h_all, hmg_all, dt_all, dtip, dyo;
+    DevBuf<affine_t> dD, dE, Cdiff, dL, dR;
+    DevBuf<xyzz_t> acc;
+    DevBuf<uint8_t> d_prefix;
+    VK_TRY(g_all.alloc(ctx, K * N));
+    VK_TRY(h_all.alloc(ctx, K * N));
+    VK_TRY(hmg_all.alloc(ctx, K * N));
+    VK_TRY(dD.alloc(ctx, K));
+    VK_TRY(dE.alloc(ctx, K));
+    VK_TRY(Cdiff.alloc(ctx, K));
+    VK_TRY(acc.alloc(ctx, K));
+    std::vector<cudaEvent_t> evs;
+    auto cleanup = [&] {
+        for (auto e : evs) cudaEventDestroy(e);
+        ctx->stream = main_stream;
+    };
+    auto fork = [&]() -> int32_t {
+        cudaEvent_t e;
+        VK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+        VK_CUDA(cudaEventRecord(e, main_stream));
+        for (size_t j = 0; j < n_side; ++j) VK_CUDA(cudaStreamWaitEvent(ctx->side_streams[j], e, 0));
+        return VKZG_OK;
+    };
+    auto join = [&]() -> int32_t {
+        for (size_t j = 0; j < n_side; ++j) {
+            cudaEvent_t e;
+            VK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            evs.push_back(e);
+            VK_CUDA(cudaEventRecord(e, ctx->side_streams[j]));
+            VK_CUDA(cudaStreamWaitEvent(main_stream, e, 0));
+        }
+        return VKZG_OK;
+    };
+#define MP_TRY(expr)                  \
+    do {                              \
+        int32_t _s = (expr);          \
+        if (_s != VKZG_OK) {          \
+            cleanup();                \
+            return _s;                \
+        }                             \
+    } while (0)
+    // ---- phase 2 (side streams): r^q, segmented row sums, quotients, g_k          multiproof.rs:117-148
+    MP_TRY(fork());
+    for (uint64_t i = 0; i < K; ++i) {
+        MpProof& p = *P[i];
+        ctx->stream = ctx->side_streams[i % n_side];
+        cudaStream_t s = ctx->stream;
+        MP_TRY(upload(ctx, p.d_order, p.order.data(), p.m));
+        MP_TRY(upload(ctx, p.d_seg_ptr, p.seg_ptr.data(), p.seg_ptr.size()));
+        MP_TRY(upload(ctx, p.d_grp_ptr, p.grp_ptr.data(), p.grp_ptr.size()));
+        MP_TRY(upload(ctx, p.d_zf, p.zf.data(), p.n_groups));
+        MP_TRY(p.rpow.alloc(ctx, p.m));
+        MP_TRY(p.partial.alloc(ctx, (size_t)p.n_segs * N));
+        MP_TRY(p.total.alloc(ctx, (size_t)p.n_groups * N));
+        MP_TRY(p.quo.alloc(ctx, (size_t)p.n_groups * N));
+        MP_TRY(p.inv.alloc(ctx, p.n_groups));
+        MP_TRY(p.dy.alloc(ctx, p.n_groups));
+        k_powers<<<ceil_div_u64(p.m, 128), 128, 0, s>>>(p.r, p.m, p.rpow);
+        MP_TRY(launch_check(ctx));
+        dim3 gs((N + 127) / 128, p.n_segs), gg((N + 127) / 128, p.n_groups);
+        k_mp_segments<<<gs, 128, 0, s>>>(df + p.off * N, p.rpow, p.d_seg_ptr, p.d_order, N, p.partial);
+        MP_TRY(launch_check(ctx));
+        k_mp_groups<<<gg, 128, 0, s>>>(p.partial, p.d_grp_ptr, N, p.total);
+        MP_TRY(launch_check(ctx));
+        MP_TRY(poly_batch(ctx, *k, p.total, N, 0, p.d_zf, p.n_groups, p.quo, p.dy, false));
+        k_mp_colsum<<<(N * 32 + 127) / 128, 128, 0, s>>>(p.quo, p.n_groups, N, g_all.p + i * N);
+        MP_TRY(launch_check(ctx));
+    }
+    ctx->stream = main_stream;
+    MP_TRY(join());
+    // D_k = commit(g_k): one K-job launch
+    MP_TRY(fixed_base_msm(ctx, *k, g_all, N, K, 0, 0xffffffffu, acc));
+    MP_TRY(normalize_points(ctx, acc, K, dD));
+    std::vector<affine_t> hD(K), hE(K);
+    MP_TRY(download(ctx, hD.data(), dD.p, K));
+    MP_TRY(stream_sync(ctx));
+    // ---- phase 3 (host): t_k                                                      multiproof.rs:150-155
+    std::vector<fp_t> tv(K);
+    for (uint64_t i = 0; i < K; ++i) {
+        P[i]->tr.append_point(hD[i], "D");
+        tv[i] = P[i]->t = P[i]->tr.digest("t");
+    }
+    MP_TRY(upload(ctx, dt_all, tv.data(), K));
+    // ---- phase 4 (side streams): 1/(t - z), h_k, h_k - g_k                        multiproof.rs:157-171
+    MP_TRY(fork());
+    for (uint64_t i = 0; i < K; ++i) {
+        MpProof& p = *P[i];
+        ctx->stream = ctx->side_streams[i % n_side];
+        cudaStream_t s = ctx->stream;
+        k_mp_inv<<<ceil_div_u64(((uint64_t)p.n_groups + 255) / 256 * 32, 128), 128, 0, s>>>(p.t, p.d_zf, p.n_groups, p.inv);
+        MP_TRY(launch_check(ctx));
+        k_mp_h<<<(N * 32 + 127) / 128, 128, 0, s>>>(p.total, p.inv, p.n_groups, N, g_all.p + i * N, h_all.p + i * N, hmg_all.p + i * N);
+        MP_TRY(launch_check(ctx));
+    }
+    ctx->stream = main_stream;
+    MP_TRY(join());
+    MP_TRY(fixed_base_msm(ctx, *k, h_all, N, K, 0, 0xffffffffu, acc));
+    MP_TRY(normalize_points(ctx, acc, K, dE));
+    k_point_sub_many<<<ceil_div_u64(K, 64), 64, 0, main_stream>>>(dE, dD, K, Cdiff);
+    MP_TRY(launch_check(ctx));
+    MP_TRY(download(ctx, hE.data(), dE.p, K));
+    MP_TRY(stream_sync(ctx));
+    // ---- phase 5 (host): every proof's transcript state after E — the prefix its inner opening continues
+    uint32_t plen = 0;
+    std::vector<uint8_t> prefixes;
+    for (uint64_t i = 0; i < K; ++i) {
+        P[i]->tr.append_point(hE[i], "E");
+        if (i == 0) {
+            plen = (uint32_t)P[i]->tr.state.size();
+            prefixes.resize((size_t)plen * K);
+        }
+        memcpy(prefixes.data() + (size_t)i * plen, P[i]->tr.state.data(), plen);  // (same length for every proof: 32 + 1 + 1 + 32)
+    }
+    MP_TRY(upload(ctx, d_prefix, prefixes.data(), prefixes.size()));
+    // ---- phase 6: the K inner openings as ONE batch                               multiproof.rs:171-174
+    MP_TRY(dyo.alloc(ctx, K));
+    memcpy(D, hD.data(), K * sizeof(affine_t));
+    if (scheme == 0) {
+        MP_TRY(dL.alloc(ctx, K * rounds));
+        MP_TRY(dR.alloc(ctx, K * rounds));
+        MP_TRY(dtip.alloc(ctx, K));
+        MP_TRY(ipa_prove_core(ctx, *k, 0, N, hmg_all, dt_all, Cdiff, K, nullptr, 0, "multiproof", dL, dR, dtip, dyo, d_prefix, plen));
+        MP_TRY(download(ctx, L, dL.p, K * rounds));
+        MP_TRY(download(ctx, R, dR.p, K * rounds));
+        MP_TRY(download(ctx, tip, dtip.p, K));
+    } else {
+        MP_TRY(dL.alloc(ctx, K));
+        MP_TRY(kzg_open_core(ctx, *k, hmg_all, N, 0, dt_all, K, dL, dyo, true));
+        MP_TRY(download(ctx, L, dL.p, K));
+    }
+    MP_TRY(download(ctx, yout, dyo.p, K));
+    int32_t st = stream_sync(ctx);
+    for (size_t j = 0; j < n_side; ++j) cudaStreamSynchronize(ctx->side_streams[j]);
+    cleanup();
+    return st;
+#undef MP_TRY
+}
+
+extern "C" {
+
+int32_t vkzg_multiproof_prove_batch(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,
+                                    const uint64_t* z, const vkzg_fr* y, const uint64_t* m_each, uint64_t K, vkzg_g1_affine* D,
+                                    vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+    return multiproof_prove_batch_impl(ctx, key_id, scheme, f, false, C, z, y, m_each, K, D, L, R, tip, yout);
+}
+int32_t vkzg_multiproof_prove_batch_dev(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* d_f, const vkzg_g1_affine* C,
+                                        const uint64_t* z, const vkzg_fr* y, const uint64_t* m_each, uint64_t K, vkzg_g1_affine* D,
+                                        vkzg_g1_affine* L, vkzg_g1_affine* R, vkzg_fr* tip, vkzg_fr* yout) {
+    return multiproof_prove_batch_impl(ctx, key_id, scheme, d_f, true, C, z, y, m_each, K, D, L, R, tip, yout);
 }
 
 int32_t vkzg_multiproof_prove(vkzg_ctx* ctx, uint32_t key_id, int32_t scheme, const vkzg_fr* f, const vkzg_g1_affine* C,

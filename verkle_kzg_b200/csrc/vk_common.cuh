@@ -71,6 +71,7 @@ struct vkzg_ctx {
     // every k_fixed_base_msm / k_msm_bucket launch on this context's stream
     cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
     cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
+    std::vector<cudaStream_t> side_streams;  // batched multiproofs: the per-proof row kernels of different proofs overlap
     bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
     bool multiproof_check_y = false;     // VKZG_OPT_MULTIPROOF_CHECK_Y (diagnostic, see include/vkzg.h)
     cudaMemPool_t pool = nullptr;        // private stream-ordered scratch pool (api.cu: ctx_create)
@@ -246,7 +247,7 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
 int32_t barycentric_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_points, uint64_t B, fp_t* d_out);
 int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const fp_t* d_a, const fp_t* d_points,
                        const affine_t* d_C, uint64_t B, const uint8_t* prefix, uint32_t prefix_len, const char* dst, affine_t* d_L,
-                       affine_t* d_R, fp_t* d_tip, fp_t* d_y);
+                       affine_t* d_R, fp_t* d_tip, fp_t* d_y, const uint8_t* d_prefix_each = nullptr, uint32_t each_len = 0);
 int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, int mode, const fp_t* d_points, const affine_t* d_C, uint64_t B, const uint8_t* prefix,
                         uint32_t prefix_len, const char* dst, const affine_t* d_L, const affine_t* d_R, const fp_t* d_tip,
                         const fp_t* d_y, int32_t* d_ok);

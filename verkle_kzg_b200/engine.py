@@ -330,6 +330,31 @@ class Engine:
                                             hptr(yo)), "vkzg_multiproof_prove")
         return dict(D=D, L=L, R=R, tip=tip, y=yo)
 
+    def multiproof_prove_batch(self, key, scheme, f, C, z, y, m_each):
+        """K multiproofs in one call: f [sum m, N, 32], C [sum m, 64], z [sum m], y [sum m, 32], m_each [K] -> list of K proof dicts"""
+        f = u8(f, 32)
+        total, N = f.shape[0], f.shape[1]
+        assert N == key.n
+        m_each = np.ascontiguousarray(m_each, dtype=np.uint64)
+        K = len(m_each)
+        assert int(m_each.sum()) == total
+        C = u8(C, 64).reshape(total, 64)
+        y = u8(y, 32).reshape(total, 32)
+        z = np.ascontiguousarray(z, dtype=np.uint64).reshape(total)
+        lg = key.log2n
+        D = np.zeros((K, 64), dtype=np.uint8)
+        L = np.zeros((K, lg, 64), dtype=np.uint8)
+        R = np.zeros((K, lg, 64), dtype=np.uint8)
+        tip = np.zeros((K, 32), dtype=np.uint8)
+        yo = np.zeros((K, 32), dtype=np.uint8)
+        Lk = L if scheme == "ipa" else np.zeros((K, 64), dtype=np.uint8)   # KZG: one proof point per multiproof
+        check(self._L.vkzg_multiproof_prove_batch(self._ctx, ctypes.c_uint32(key.id), ctypes.c_int32(0 if scheme == "ipa" else 1), hptr(f),
+                                                  hptr(C), hptr(z), hptr(y), hptr(m_each), ctypes.c_uint64(K), hptr(D), hptr(Lk), hptr(R),
+                                                  hptr(tip), hptr(yo)), "vkzg_multiproof_prove_batch")
+        if scheme != "ipa":
+            L[:, 0] = Lk
+        return [dict(D=D[i], L=L[i], R=R[i], tip=tip[i], y=yo[i]) for i in range(K)]
+
     def multiproof_verify_ipa(self, key, C, z, y, proof):
         C = u8(C, 64).reshape(-1, 64)
         m = len(C)
