@@ -321,56 +321,6 @@ def run_reference(args):
         reps = min(cores, 4)
         per_step = reps
         fn = lambda: cpu_multiproof_sample(bases, m, cores, reps=reps)
-    elif wl == "mpbatch":
-        m = 1 << 12                                                             # configs[2] at a batch: K multiproofs of 2^12 openings in one call
-        K = args.batch or 64
-        key = ctx.key257(c)
-        gen.manual_seed(0x5EED3100 + rank)
-        tot = K * m
-        f = rand_fr_dev(torch, tot * N_WIDTH, gen).reshape(tot, N_WIDTH, 32)
-        zi = torch.randint(0, N_WIDTH, (tot,), device="cuda", generator=gen)
-        Cq = torch.empty((tot, 64), dtype=torch.uint8, device="cuda")
-        eng.commit_batch_dev(key, f, N_WIDTH, tot, Cq)
-        yq = f[torch.arange(tot, device="cuda"), zi].contiguous()
-        f_h = pinned(torch, (tot, N_WIDTH, 32))
-        f_h.copy_(f)
-        C_h, y_h = Cq.cpu().contiguous(), yq.cpu().contiguous()
-        z_h = zi.cpu().numpy().astype(np.uint64)
-        me = np.full(K, m, dtype=np.uint64)
-        D_h, L_h, R_h = pinned(torch, (K, 64)), pinned(torch, (K, 8, 64)), pinned(torch, (K, 8, 64))
-        tip_h, yo_h = pinned(torch, (K, 32)), pinned(torch, (K, 32))
-        kid = ctypes.c_uint32(key.id)
-        zp, mp_ = z_h.ctypes.data_as(ctypes.c_void_p), me.ctypes.data_as(ctypes.c_void_p)
-
-        def step():
-            check(L.vkzg_multiproof_prove_batch_dev(eng._ctx, kid, ctypes.c_int32(0), ctypes.c_void_p(f.data_ptr()), hp(C_h), zp, hp(y_h), mp_,
-                                                    ctypes.c_uint64(K), hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_batch_dev")
-
-        def step_e2e():
-            check(L.vkzg_multiproof_prove_batch(eng._ctx, kid, ctypes.c_int32(0), hp(f_h), hp(C_h), zp, hp(y_h), mp_, ctypes.c_uint64(K),
-                                                hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_batch")
-
-        def checker():
-            """every multiproof of the batch through the device verifier; the first and the last against the oracle"""
-            orc = _orc()
-            Cn, yn, fn = C_h.numpy(), y_h.numpy(), f_h.numpy()
-            for i in range(K):
-                pr = dict(D=D_h.numpy()[i], L=L_h.numpy()[i], R=R_h.numpy()[i], tip=tip_h.numpy()[i], y=yo_h.numpy()[i])
-                sl = slice(i * m, (i + 1) * m)
-                _need(eng.multiproof_verify_ipa(key, Cn[sl], z_h[sl], yn[sl], pr), f"multiproof {i} of the batch fails the device verifier")
-                if i in (0, K - 1):
-                    exp = orc.multiproof_prove("ipa", ctx.bases_h, N_WIDTH, fn[sl], Cn[sl], z_h[sl], yn[sl])
-                    _need(all((pr[k] == exp[k]).all() for k in pr), f"multiproof {i} differs from the oracle's")
-            return {"verified": K, "oracle_samples": min(K, 2)}
-        reps = min(cores, 4)
-        w.update(step=step, step_e2e=step_e2e, check=checker, units=K,
-                 madds=(2 * N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * W,
-                 h2d=f_h.numel() + tot * (64 + 8 + 32), d2h=K * (64 + 2 * 8 * 64 + 64),
-                 metric="ipa_multiproofs_per_s", unit="multiproofs/s",
-                 cfg={"workload": f"configs[2] in bulk: {K} IPA multiproofs of {m} openings each (width 256) per call (vkzg_multiproof_prove_batch)",
-                      "openings_per_multiproof": m, "multiproofs_per_call": K},
-                 cpu=lambda: cpu_multiproof_sample(ctx.bases_h, m, cores, reps=reps) + (f"{reps} multiproofs of {m} openings side by side",))
-
     elif wl == "tree":
         per_step = 256 * cores
         bases = reference_bases(N_WIDTH + 1)
@@ -694,6 +644,56 @@ def build_workload(ctx, wl, c):
                  metric="ipa_multiproofs_per_s", unit="multiproofs/s",
                  cfg={"workload": f"configs[2]: IPA multiproof aggregating {m} openings at width 256 (one multiproof per step per GPU; replicas across GPUs)",
                       "openings_per_multiproof": m},
+                 cpu=lambda: cpu_multiproof_sample(ctx.bases_h, m, cores, reps=reps) + (f"{reps} multiproofs of {m} openings side by side",))
+
+    elif wl == "mpbatch":
+        m = 1 << 12                                                             # configs[2] at a batch: K multiproofs of 2^12 openings in one call
+        K = args.batch or 64
+        key = ctx.key257(c)
+        gen.manual_seed(0x5EED3100 + rank)
+        tot = K * m
+        f = rand_fr_dev(torch, tot * N_WIDTH, gen).reshape(tot, N_WIDTH, 32)
+        zi = torch.randint(0, N_WIDTH, (tot,), device="cuda", generator=gen)
+        Cq = torch.empty((tot, 64), dtype=torch.uint8, device="cuda")
+        eng.commit_batch_dev(key, f, N_WIDTH, tot, Cq)
+        yq = f[torch.arange(tot, device="cuda"), zi].contiguous()
+        f_h = pinned(torch, (tot, N_WIDTH, 32))
+        f_h.copy_(f)
+        C_h, y_h = Cq.cpu().contiguous(), yq.cpu().contiguous()
+        z_h = zi.cpu().numpy().astype(np.uint64)
+        me = np.full(K, m, dtype=np.uint64)
+        D_h, L_h, R_h = pinned(torch, (K, 64)), pinned(torch, (K, 8, 64)), pinned(torch, (K, 8, 64))
+        tip_h, yo_h = pinned(torch, (K, 32)), pinned(torch, (K, 32))
+        kid = ctypes.c_uint32(key.id)
+        zp, mp_ = z_h.ctypes.data_as(ctypes.c_void_p), me.ctypes.data_as(ctypes.c_void_p)
+
+        def step():
+            check(L.vkzg_multiproof_prove_batch_dev(eng._ctx, kid, ctypes.c_int32(0), ctypes.c_void_p(f.data_ptr()), hp(C_h), zp, hp(y_h), mp_,
+                                                    ctypes.c_uint64(K), hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_batch_dev")
+
+        def step_e2e():
+            check(L.vkzg_multiproof_prove_batch(eng._ctx, kid, ctypes.c_int32(0), hp(f_h), hp(C_h), zp, hp(y_h), mp_, ctypes.c_uint64(K),
+                                                hp(D_h), hp(L_h), hp(R_h), hp(tip_h), hp(yo_h)), "multiproof_batch")
+
+        def checker():
+            """every multiproof of the batch through the device verifier; the first and the last against the oracle"""
+            orc = _orc()
+            Cn, yn, fn = C_h.numpy(), y_h.numpy(), f_h.numpy()
+            for i in range(K):
+                pr = dict(D=D_h.numpy()[i], L=L_h.numpy()[i], R=R_h.numpy()[i], tip=tip_h.numpy()[i], y=yo_h.numpy()[i])
+                sl = slice(i * m, (i + 1) * m)
+                _need(eng.multiproof_verify_ipa(key, Cn[sl], z_h[sl], yn[sl], pr), f"multiproof {i} of the batch fails the device verifier")
+                if i in (0, K - 1):
+                    exp = orc.multiproof_prove("ipa", ctx.bases_h, N_WIDTH, fn[sl], Cn[sl], z_h[sl], yn[sl])
+                    _need(all((pr[k] == exp[k]).all() for k in pr), f"multiproof {i} differs from the oracle's")
+            return {"verified": K, "oracle_samples": min(K, 2)}
+        reps = min(cores, 4)
+        w.update(step=step, step_e2e=step_e2e, check=checker, units=K,
+                 madds=(2 * N_WIDTH + 8 * 2 * (N_WIDTH // 2 + 1)) * W,
+                 h2d=f_h.numel() + tot * (64 + 8 + 32), d2h=K * (64 + 2 * 8 * 64 + 64),
+                 metric="ipa_multiproofs_per_s", unit="multiproofs/s",
+                 cfg={"workload": f"configs[2] in bulk: {K} IPA multiproofs of {m} openings each (width 256) per call (vkzg_multiproof_prove_batch)",
+                      "openings_per_multiproof": m, "multiproofs_per_call": K},
                  cpu=lambda: cpu_multiproof_sample(ctx.bases_h, m, cores, reps=reps) + (f"{reps} multiproofs of {m} openings side by side",))
 
     elif wl == "tree":
