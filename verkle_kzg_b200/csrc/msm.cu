@@ -9,9 +9,7 @@
 //   4. k_msm_bucket   P lanes per bucket (P adjacent lanes, interleaved slices -> equal work), 64-byte
 //                     vectorised gathers one entry ahead of the mixed addition, shuffle-tree fold of the
 //                     P partial sums
-//   5. k_msm_reduce   weighted bucket sum: per-thread running sums over 8 buckets, a small scalar multiple
-//                     for the segment offset, shared-memory tree per CTA
-//   6. k_xyzz_sum     CTA results -> one point, then the common normalisation kernel
+//   5. k_msm_bitsums + k_msm_bitcombine   weighted bucket sum, bit-parallel (see below), then the common normalisation
 // The order in which a bucket's points are added is not deterministic (atomics), the result is: it leaves
 // the device in canonical affine form.
 #include "vk_common.cuh"
@@ -163,61 +161,72 @@ __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restric
     }
 }
 
-__device__ __noinline__ xyzz_t xyzz_mul_small(const xyzz_t p, uint32_t k) {
+// ---------------------------------------------------------------------------------------------------------------
+// Weighted bucket sum  sum_b (b + 1) B_b.  This tail is a chain of DEPENDENT point operations (each ~10 k cycles for a
+// lone warp, whatever the GPU has idle), so it is organised for depth, not for work: with w = b + 1 written in binary,
+//     sum_b w_b B_b = sum_j 2^j T_j ,   T_j = sum of the buckets whose weight has bit j set,
+// every T_j is a PLAIN sum (tree, no running sums, no per-segment scalar multiple): k_msm_bitsums — one CTA per
+// (bit, slice of 2048 buckets): <= 4 additions per thread + a pair-split shuffle tree + 3 shared-memory levels;
+// k_msm_bitcombine — warp j folds the slice sums of bit j, doubles j times, the c values are summed.  ~35 dependent
+// operations, most of them doublings or pair-split additions, against the ~52 full additions of the running-sum form
+// (measured at n = 2^16: 325 -> see profiles/ us for the two kernels).
+// ---------------------------------------------------------------------------------------------------------------
+static const int BS_THREADS = 256;
+static const int BS_SLICE = 2048;  // buckets per CTA
+
+__global__ void __launch_bounds__(BS_THREADS) k_msm_bitsums(const xyzz_t* __restrict__ buckets, uint32_t nb, uint32_t slices,
+                                                            xyzz_t* __restrict__ out /*[bits][slices]*/) {
+    __shared__ xyzz_t sh[BS_THREADS / 32];
+    const uint32_t bit = blockIdx.y, slice = blockIdx.x;
+    const uint32_t lo = slice * BS_SLICE;
     xyzz_t acc = xyzz_inf();
-    if (k == 0) return acc;
-    int top = 31 - __clz(k);
-    for (int b = top; b >= 0; --b) {
-        acc = xyzz_dbl_ni(acc);
-        if ((k >> b) & 1) acc = xyzz_add_ni(acc, p);
-    }
-    return acc;
-}
-
-static const int RED_SEG = 8;
-static const int RED_THREADS = 128;
-
-// sum_b (b + 1) B_b: thread = segment of RED_SEG buckets, CTA tree, one XYZZ per CTA
-__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(const xyzz_t* __restrict__ buckets, uint32_t nb, xyzz_t* __restrict__ out) {
-    __shared__ xyzz_t sh[RED_THREADS];
-    uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;
-    uint32_t lo = seg * RED_SEG;
-    xyzz_t run = xyzz_inf(), sum = xyzz_inf();
-    if (lo < nb) {
-        uint32_t hi = lo + RED_SEG < nb ? lo + RED_SEG : nb;
 #pragma unroll 1
-        for (uint32_t b = hi; b-- > lo;) {
+    for (uint32_t i = threadIdx.x; i < BS_SLICE; i += BS_THREADS) {
+        uint32_t b = lo + i;
+        if (b < nb && (((b + 1) >> bit) & 1)) {
             xyzz_t B;
             B.x = fp_load(&buckets[b].x);
             B.y = fp_load(&buckets[b].y);
             B.zz = fp_load(&buckets[b].zz);
             B.zzz = fp_load(&buckets[b].zzz);
-            run = xyzz_add_ni(run, B);
-            sum = xyzz_add_ni(sum, run);
+            acc = xyzz_add_ni(acc, B);
         }
-        // weights inside the segment were 1..RED_SEG; the true ones are lo + 1 .. lo + RED_SEG
-        if (lo) sum = xyzz_add_ni(sum, xyzz_mul_small(run, lo));
     }
-    sh[threadIdx.x] = sum;
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) acc = xyzz_add_pair(acc, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
-    for (int off = RED_THREADS / 2; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
-        __syncthreads();
+    if (threadIdx.x < 32) {
+        xyzz_t v = threadIdx.x < BS_THREADS / 32 ? sh[threadIdx.x] : xyzz_inf();
+#pragma unroll 1
+        for (int off = 1; off < BS_THREADS / 32; off <<= 1) v = xyzz_add_pair(v, off);
+        if (threadIdx.x == 0) out[bit * slices + slice] = v;
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
-__global__ void __launch_bounds__(256) k_xyzz_sum(const xyzz_t* __restrict__ pts, uint32_t n, xyzz_t* __restrict__ out) {
-    __shared__ xyzz_t sh[256];
-    xyzz_t acc = xyzz_inf();
-    for (uint32_t i = threadIdx.x; i < n; i += 256) acc = xyzz_add_ni(acc, pts[i]);
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
-        __syncthreads();
+// one CTA, warp j <-> bit j (bits <= 32 warps): fold the slice sums (lanes), 2^j by j doublings, sum over the warps
+__global__ void __launch_bounds__(1024) k_msm_bitcombine(const xyzz_t* __restrict__ part, uint32_t bits, uint32_t slices,
+                                                         xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    xyzz_t v = xyzz_inf();
+    if (warp < bits)
+        for (uint32_t sidx = lane; sidx < slices; sidx += 32) v = xyzz_add_ni(v, part[warp * slices + sidx]);
+    uint32_t span = slices < 32 ? slices : 32;
+#pragma unroll 1
+    for (uint32_t off = 1; off < span; off <<= 1) v = xyzz_add_pair(v, (int)off);
+    if (lane == 0) {
+#pragma unroll 1
+        for (uint32_t j = 0; j < warp && warp < bits; ++j) v = xyzz_dbl_ni(v);
+        sh[warp] = warp < bits ? v : xyzz_inf();
     }
-    if (threadIdx.x == 0) out[0] = sh[0];
+    __syncthreads();
+    if (warp == 0) {
+        xyzz_t t = lane < bits ? sh[lane] : xyzz_inf();
+#pragma unroll 1
+        for (int off = 1; off < 32; off <<= 1) t = xyzz_add_pair(t, off);
+        if (lane == 0) out[0] = t;
+    }
 }
 
 int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out) {
@@ -287,13 +296,13 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets, gate, 1);
     }
     VK_TRY(launch_check(ctx));
-    uint32_t segs = (nb + RED_SEG - 1) / RED_SEG;
-    uint32_t rblocks = (segs + RED_THREADS - 1) / RED_THREADS;
-    VK_TRY(partial.alloc(ctx, rblocks + 1));
-    k_msm_reduce<<<rblocks, RED_THREADS, 0, s>>>(buckets, nb, partial);
+    const uint32_t bits = k.c, slices = (nb + BS_SLICE - 1) / BS_SLICE;  // weights 1 .. 2^(c-1): c bits
+    VK_TRY(partial.alloc(ctx, (size_t)bits * slices + 1));
+    k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(buckets, nb, slices, partial);
     VK_TRY(launch_check(ctx));
-    k_xyzz_sum<<<1, 256, 0, s>>>(partial, rblocks, partial.p + rblocks);
+    k_msm_bitcombine<<<1, 32 * bits, 0, s>>>(partial, bits, slices, partial.p + (size_t)bits * slices);
     VK_TRY(launch_check(ctx));
+    const uint32_t rblocks = bits * slices;
     return normalize_points(ctx, partial.p + rblocks, 1, d_out);
 }
 
