@@ -597,7 +597,9 @@ def build_workload(ctx, wl, c):
         def cleanup():
             key.free()
         nsmp = 128 * cores
-        w.update(step=step, step_e2e=step_e2e, check=checker, cleanup=cleanup, madds=16, units=per, h2d=s_h.numel(), d2h=64,
+        msm_windows = int(round(key.table_bytes / 64 / per))                   # digits per scalar of this key (16 at c = 16, 20 at c = 13)
+        w["extra"]["msm_windows"] = msm_windows
+        w.update(step=step, step_e2e=step_e2e, check=checker, cleanup=cleanup, madds=msm_windows, units=per, h2d=s_h.numel(), d2h=64,
                  kernel="k_msm_bucket", scaling="strong" if world > 1 else "weak",
                  metric="msm_points_per_s", unit="points/s",
                  cfg={"workload": f"configs[3]: one KZG-commit MSM of 2^{args.log2n} points, point-range sharded over {world} GPU(s)"

@@ -171,7 +171,9 @@ int32_t vkzg_key_load_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_bases, uint32_t
     k.has_q = d_q != nullptr;
     if (kind == VKZG_KEY_MSM && d_q) return VKZG_ERR_ARG;
     uint32_t c = window_bits;
-    if (c == 0) c = kind == VKZG_KEY_WINDOW ? 16 : (n >= (1u << 14) ? 16 : 12);
+    // MSM keys: the weighted bucket sum is a latency-bound tail whose cost grows with the 2^(c-1) buckets, the bucket pass with
+    // the ceil(256/c) digits per scalar: 16 from 2^18 points on, 13 for the 2^14 .. 2^17-point slices of a sharded MSM
+    if (c == 0) c = kind == VKZG_KEY_WINDOW ? 16 : (n >= (1u << 18) ? 16 : (n >= (1u << 14) ? 13 : 12));
     if (c < 2 || c > 20) return VKZG_ERR_ARG;
     k.c = c;
     k.W = (256 + c - 1) / c;

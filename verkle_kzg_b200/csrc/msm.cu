@@ -229,6 +229,65 @@ __global__ void __launch_bounds__(1024) k_msm_bitcombine(const xyzz_t* __restric
     }
 }
 
+// ---- running-sum form of the weighted bucket sum: less work (2 additions per bucket), longer chain — used for large bucket
+//      sets (nb > 8192), where the bit-parallel form above is bound by its 16x redundant additions, not by its depth
+__device__ __noinline__ xyzz_t xyzz_mul_small(const xyzz_t p, uint32_t k) {
+    xyzz_t acc = xyzz_inf();
+    if (k == 0) return acc;
+    int top = 31 - __clz(k);
+    for (int b = top; b >= 0; --b) {
+        acc = xyzz_dbl_ni(acc);
+        if ((k >> b) & 1) acc = xyzz_add_ni(acc, p);
+    }
+    return acc;
+}
+
+static const int RED_SEG = 8;
+static const int RED_THREADS = 128;
+
+// sum_b (b + 1) B_b: thread = segment of RED_SEG buckets, CTA tree, one XYZZ per CTA
+__global__ void __launch_bounds__(RED_THREADS) k_msm_reduce(const xyzz_t* __restrict__ buckets, uint32_t nb, xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[RED_THREADS];
+    uint32_t seg = blockIdx.x * RED_THREADS + threadIdx.x;
+    uint32_t lo = seg * RED_SEG;
+    xyzz_t run = xyzz_inf(), sum = xyzz_inf();
+    if (lo < nb) {
+        uint32_t hi = lo + RED_SEG < nb ? lo + RED_SEG : nb;
+#pragma unroll 1
+        for (uint32_t b = hi; b-- > lo;) {
+            xyzz_t B;
+            B.x = fp_load(&buckets[b].x);
+            B.y = fp_load(&buckets[b].y);
+            B.zz = fp_load(&buckets[b].zz);
+            B.zzz = fp_load(&buckets[b].zzz);
+            run = xyzz_add_ni(run, B);
+            sum = xyzz_add_ni(sum, run);
+        }
+        // weights inside the segment were 1..RED_SEG; the true ones are lo + 1 .. lo + RED_SEG
+        if (lo) sum = xyzz_add_ni(sum, xyzz_mul_small(run, lo));
+    }
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = RED_THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(256) k_xyzz_sum(const xyzz_t* __restrict__ pts, uint32_t n, xyzz_t* __restrict__ out) {
+    __shared__ xyzz_t sh[256];
+    xyzz_t acc = xyzz_inf();
+    for (uint32_t i = threadIdx.x; i < n; i += 256) acc = xyzz_add_ni(acc, pts[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] = xyzz_add_ni(sh[threadIdx.x], sh[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
 int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out) {
     const uint32_t nb = 1u << (k.c - 1);
     DevBuf<uint32_t> counts, offsets, entries;
@@ -296,13 +355,25 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets, gate, 1);
     }
     VK_TRY(launch_check(ctx));
-    const uint32_t bits = k.c, slices = (nb + BS_SLICE - 1) / BS_SLICE;  // weights 1 .. 2^(c-1): c bits
-    VK_TRY(partial.alloc(ctx, (size_t)bits * slices + 1));
-    k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(buckets, nb, slices, partial);
-    VK_TRY(launch_check(ctx));
-    k_msm_bitcombine<<<1, 32 * bits, 0, s>>>(partial, bits, slices, partial.p + (size_t)bits * slices);
-    VK_TRY(launch_check(ctx));
-    const uint32_t rblocks = bits * slices;
+    uint32_t rblocks;
+    if (nb <= 8192) {
+        // measured at n = 2^16 (B200): c = 16 / running sums 325 us for this tail; c = 13 / bit-parallel see DESIGN.md
+        const uint32_t bits = k.c, slices = (nb + BS_SLICE - 1) / BS_SLICE;  // weights 1 .. 2^(c-1): c bits
+        rblocks = bits * slices;
+        VK_TRY(partial.alloc(ctx, (size_t)rblocks + 1));
+        k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(buckets, nb, slices, partial);
+        VK_TRY(launch_check(ctx));
+        k_msm_bitcombine<<<1, 32 * bits, 0, s>>>(partial, bits, slices, partial.p + rblocks);
+        VK_TRY(launch_check(ctx));
+    } else {
+        uint32_t segs = (nb + RED_SEG - 1) / RED_SEG;
+        rblocks = (segs + RED_THREADS - 1) / RED_THREADS;
+        VK_TRY(partial.alloc(ctx, rblocks + 1));
+        k_msm_reduce<<<rblocks, RED_THREADS, 0, s>>>(buckets, nb, partial);
+        VK_TRY(launch_check(ctx));
+        k_xyzz_sum<<<1, 256, 0, s>>>(partial, rblocks, partial.p + rblocks);
+        VK_TRY(launch_check(ctx));
+    }
     return normalize_points(ctx, partial.p + rblocks, 1, d_out);
 }
 
