@@ -53,9 +53,15 @@ __global__ void __launch_bounds__(256) k_msm_digits(const fp_t* __restrict__ sca
 
 // Optimistic single pass: every bucket owns `cap` slots (mean size + 25 %), entries that do not fit are counted in
 // *dropped and the caller falls back to the exact two-pass counting sort (skewed scalars).
+// The TOP window holds only 254 - c (W - 1) bits, i.e. every scalar's top digit falls into the first `top_n` buckets
+// (49 of them at c = 13): those buckets get `top_extra` more slots each — list b starts at b * cap + min(b, top_n) * top_extra.
+__device__ __forceinline__ size_t msm_list_base(uint32_t b, uint32_t cap, uint32_t top_n, uint32_t top_extra) {
+    return (size_t)b * cap + (size_t)(b < top_n ? b : top_n) * top_extra;
+}
 __global__ void __launch_bounds__(256) k_msm_scatter_fixed(const fp_t* __restrict__ scalars, uint64_t n, uint32_t c, uint32_t W,
-                                                           uint32_t key_n, uint64_t first, uint32_t cap, uint32_t* __restrict__ cursor,
-                                                           uint32_t* __restrict__ entries, uint32_t* __restrict__ dropped) {
+                                                           uint32_t key_n, uint64_t first, uint32_t cap, uint32_t top_n, uint32_t top_extra,
+                                                           uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries,
+                                                           uint32_t* __restrict__ dropped) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fp_t k = fp_from_mont<S>(fp_load_ro(scalars + i));
@@ -69,8 +75,8 @@ __global__ void __launch_bounds__(256) k_msm_scatter_fixed(const fp_t* __restric
         if (mag) {
             uint32_t b = mag - 1;
             uint32_t pos = atomicAdd(cursor + b, 1u);
-            if (pos < cap)
-                entries[(size_t)b * cap + pos] = (uint32_t)((uint64_t)w * key_n + first + i) | (neg << 31);
+            if (pos < cap + (b < top_n ? top_extra : 0u))
+                entries[msm_list_base(b, cap, top_n, top_extra) + pos] = (uint32_t)((uint64_t)w * key_n + first + i) | (neg << 31);
             else
                 ++lost;
         }
@@ -115,15 +121,16 @@ __global__ void __launch_bounds__(256) k_msm_clear_if(uint32_t* __restrict__ cou
 // P (power of two <= 32) adjacent lanes per bucket
 __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                     const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P, uint32_t cap,
-                                                    xyzz_t* __restrict__ buckets, const uint32_t* __restrict__ gate, uint32_t gate_want) {
+                                                    uint32_t top_n, uint32_t top_extra, xyzz_t* __restrict__ buckets,
+                                                    const uint32_t* __restrict__ gate, uint32_t gate_want) {
     if (gate && (*gate != 0) != (gate_want != 0)) return;
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = (uint32_t)(t / P), p = (uint32_t)(t % P);
     bool live = b < nb;
-    uint32_t lo = 0, hi = 0;
+    size_t lo = 0, hi = 0;
     if (live) {
         if (cap) {  // fixed-capacity layout: offsets[] holds the bucket sizes
-            lo = b * cap;
+            lo = msm_list_base(b, cap, top_n, top_extra);
             hi = lo + offsets[b];
         } else {
             lo = offsets[b];
@@ -131,14 +138,16 @@ __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restric
         }
     }
     xyzz_t acc = xyzz_inf();
-    uint32_t i = lo + p, e = 0;
+    size_t i = lo + p;
+    uint32_t e = 0;
     affine_t cur;
     if (i < hi) {
         e = __ldg(entries + i);
         cur = load_affine_ro2(table + (e & 0x7fffffffu));
     }
     while (i < hi) {
-        uint32_t in = i + P, en = 0;
+        size_t in = i + P;
+        uint32_t en = 0;
         affine_t nxt;
         if (in < hi) {
             en = __ldg(entries + in);
@@ -315,17 +324,26 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     //      not fit are counted in *dropped (device memory); the exact two-pass counting sort below is enqueued behind it and
     //      its kernels return at once unless *dropped != 0 (skewed scalars) — no host synchronisation either way.
     uint64_t cap64 = avg + avg / 4 + 64;
-    const bool optimistic = n >= (1u << 12) && cap64 * nb < (1ull << 31) && !getenv("VKZG_MSM_TWO_PASS");
+    // top window: 254 - c (W - 1) bits; its digits are <= (r >> shift) + 1 and uniform below that
+    const uint32_t top_shift = k.c * (k.W - 1);
+    uint32_t top_n = 0, top_extra = 0;
+    if (top_shift < 254 && 254 - top_shift < k.c - 1) {
+        const uint32_t r_top = top_shift >= 224 ? (0x30644e72u >> (top_shift - 224)) : 0xffffffffu;  // r >> top_shift (r < 2^254)
+        top_n = r_top + 2 < nb ? r_top + 2 : nb;
+        uint64_t per = n / (r_top ? r_top : 1);
+        top_extra = (uint32_t)(per + per / 4 + 64);
+    }
+    const bool optimistic = n >= (1u << 12) && cap64 * nb + (uint64_t)top_n * top_extra < (1ull << 31) && !getenv("VKZG_MSM_TWO_PASS");
     const uint32_t* gate = nullptr;
     if (optimistic) {
         const uint32_t cap = (uint32_t)cap64;
         uint32_t* dropped = counts.p + nb;
-        VK_TRY(entries.alloc(ctx, (size_t)cap * nb));
-        k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, counts, entries, dropped);
+        VK_TRY(entries.alloc(ctx, (size_t)cap * nb + (size_t)top_n * top_extra));
+        k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, top_n, top_extra, counts, entries, dropped);
         VK_TRY(launch_check(ctx));
         {
             KernelTimer timer(ctx);
-            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, buckets, dropped, 0);
+            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, top_n, top_extra, buckets, dropped, 0);
         }
         VK_TRY(launch_check(ctx));
         gate = dropped;
@@ -349,10 +367,10 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         VK_TRY(launch_check(ctx));
     }
     if (gate) {  // (the optimistic launch above is the timed one)
-        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets, gate, 1);
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, 0, 0, buckets, gate, 1);
     } else {
         KernelTimer timer(ctx);
-        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, buckets, gate, 1);
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, 0, 0, buckets, gate, 1);
     }
     VK_TRY(launch_check(ctx));
     uint32_t rblocks;
