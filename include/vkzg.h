@@ -61,13 +61,16 @@ int32_t vkzg_ctx_sync(vkzg_ctx* ctx);
  * VKZG_OPT_TREE_FLATTEN (default 0 = automatic): how vkzg_tree_commit gathers the dirty nodes — 1 = always the sequential
  * bulk pass over the node array, 2 = always the depth-first walk of the dirty paths (automatic: bulk when more than an
  * eighth of the nodes is dirty).  Results are identical; the knob exists for tests and measurements.
+ * VKZG_OPT_BATCH_AFFINE (default -1 = automatic): big batches of dense width-N jobs (commits, IPA cross terms) are summed by the
+ * batch-affine tree (6 field products per addition, shared inversions) instead of per-lane XYZZ accumulators (10 products);
+ * 0 = never, 1 = whenever the shape allows.  Results are identical (canonical affine points).
  * VKZG_OPT_MULTIPROOF_CHECK_Y (default 0; diagnostic): vkzg_multiproof_verify_ipa additionally compares the proof's
  * evaluation with g2(t) = sum_q r^q y_q / (t - z_q), the sum the reference computes and never uses (multiproof.rs:201-215:
  * its verifier accepts ANY claimed y_q).  The comparison cannot be the default: the reference's prover divides by
  * (X - w^z) in g but by (t - z), z an INTEGER, in h (multiproof.rs:155-166, quirk Q4), so (h - g)(t) != g2(t) even for an
  * honest proof — with the option on, every proof made by the reference's algorithm (and by this library, which is
  * bit-exact with it) is rejected.  See DESIGN.md section 6.                                                            */
-enum { VKZG_OPT_IPA_TWO_STREAMS = 1, VKZG_OPT_TREE_FLATTEN = 2, VKZG_OPT_MULTIPROOF_CHECK_Y = 3 };
+enum { VKZG_OPT_IPA_TWO_STREAMS = 1, VKZG_OPT_TREE_FLATTEN = 2, VKZG_OPT_MULTIPROOF_CHECK_Y = 3, VKZG_OPT_BATCH_AFFINE = 4 };
 int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value);
 /* Scratch memory comes from a stream-ordered pool private to the context (the device's default pool is not touched); freed
  * blocks stay cached between calls (VKZG_POOL_KEEP_MB in the environment bounds that) — vkzg_ctx_trim synchronises and

@@ -130,6 +130,10 @@ int32_t vkzg_ctx_set_option(vkzg_ctx* ctx, int32_t option, int32_t value) {
             ctx->tree_flatten = value;
             return VKZG_OK;
         case VKZG_OPT_MULTIPROOF_CHECK_Y: ctx->multiproof_check_y = value != 0; return VKZG_OK;
+        case VKZG_OPT_BATCH_AFFINE:
+            if (value < -1 || value > 1) return VKZG_ERR_ARG;
+            ctx->batch_affine = value;
+            return VKZG_OK;
         default: return VKZG_ERR_ARG;
     }
 }

@@ -201,6 +201,18 @@ int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, u
     if (lanes_per_job == 2) return launch_fixed_base<2>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 4) return launch_fixed_base<4>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
     if (lanes_per_job == 8) return launch_fixed_base<8>(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_row_ptr, d_slot, 1, d_out);
+    // big dense batches of wide jobs: the batch-affine tree (batch_affine.cu)
+    if (!d_row_ptr && lanes_per_job == 0) {
+        static int ba_env = -2;
+        if (ba_env == -2) {
+            const char* e = getenv("VKZG_BATCH_AFFINE");
+            ba_env = e ? atoi(e) : -1;
+        }
+        const int mode = ctx->batch_affine >= 0 ? ctx->batch_affine : ba_env;
+        const bool big = jobs * (uint64_t)T * k.W >= (4ull << 20);  // >= 4 M additions: every level keeps thousands of warps busy
+        // (an explicit VKZG_OPT_BATCH_AFFINE = 1 is the caller's decision whatever the size — the tests use small batches)
+        if (mode == 1 && (big || ctx->batch_affine == 1)) return fixed_base_msm_batch_affine(ctx, k, d_scalars, T, jobs, ipa_m, q_row, d_out);
+    }
     // big dense batches: fewer lanes per job shorten the shuffle-tree fold (log2(lanes) full additions per job) as long as
     // enough warps remain to fill the GPU several times over
     if (!d_row_ptr && lanes_per_job == 0) {

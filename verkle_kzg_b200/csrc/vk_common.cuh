@@ -73,6 +73,7 @@ struct vkzg_ctx {
     cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
     std::vector<cudaStream_t> side_streams;  // batched multiproofs: the per-proof row kernels of different proofs overlap
     bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
+    int batch_affine = -1;               // VKZG_OPT_BATCH_AFFINE: -1 automatic, 0 off, 1 on (big dense batches)
     bool multiproof_check_y = false;     // VKZG_OPT_MULTIPROOF_CHECK_Y (diagnostic, see include/vkzg.h)
     cudaMemPool_t pool = nullptr;        // private stream-ordered scratch pool (api.cu: ctx_create)
     int tree_flatten = 0;                // VKZG_OPT_TREE_FLATTEN
@@ -240,6 +241,9 @@ int32_t domain_for(vkzg_ctx* ctx, uint32_t lg, const DomainTables*& dt);
 // ipa_m != 0: the L/R cross-term base selection of an IPA round (commit.cu).  Result: out_xyzz[jobs].
 int32_t fixed_base_msm(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                        uint32_t q_row, xyzz_t* d_out);
+// the same through the batch-affine tree (batch_affine.cu): dense jobs only, pays from a few thousand jobs on
+int32_t fixed_base_msm_batch_affine(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
+                                    uint32_t q_row, xyzz_t* d_out);
 // CSR variant (verkle nodes): job j owns terms [row_ptr[j], row_ptr[j+1]), term t uses base slot[t]
 int32_t fixed_base_msm_csr(vkzg_ctx* ctx, const Key& k, const fp_t* d_scalars, uint32_t T, uint64_t jobs, uint32_t ipa_m,
                            uint32_t q_row, const uint32_t* d_row_ptr, const uint16_t* d_slot, xyzz_t* d_out, uint32_t lanes_per_job,

@@ -69,6 +69,7 @@ class Engine:
 
     OPT_IPA_TWO_STREAMS = 1   # include/vkzg.h
     OPT_TREE_FLATTEN = 2      # 0 automatic, 1 bulk pass, 2 depth-first walk of the dirty paths
+    OPT_BATCH_AFFINE = 4      # -1 automatic, 0 off, 1 on: batch-affine tree for big dense batches
     OPT_MULTIPROOF_CHECK_Y = 3  # diagnostic (default 0): verify_multiproof also compares y_proof with g2(t) — see include/vkzg.h
 
     def set_option(self, option, value):
