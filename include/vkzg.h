@@ -258,6 +258,17 @@ int32_t vkzg_kzg_setup_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_powers, uint32
  * base 0 is the generator G                                                                                       */
 int32_t vkzg_kzg_powers(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* tau, uint32_t m, vkzg_g1_affine* out);
 
+/* ---- next row: IPAPointGenerator (vector-commit/src/ipa/ipa_point_generator.rs:51-81) with
+ *      EthereumHashToCurve (:97-109): candidate i = SHA-256(seed || i as 8 little-endian bytes) parsed by ark-ec's
+ *      Affine::from_random_bytes.  `gen(num)`: the first num indices 0, 1, 2 ... that give a point, in index order ->
+ *      out[num]; *next_index (may be NULL) = the first index not consumed.  The caller enforces `num <= max`
+ *      (PointGeneratorError::OutOfBounds) — the library has no notion of the generator's `max`.                          */
+int32_t vkzg_ipa_crs_generate(vkzg_ctx* ctx, const uint8_t* seed, uint64_t seed_len, uint64_t num, vkzg_g1_affine* out,
+                              uint64_t* next_index);
+/* `gen_at(index)`: *ok = 1 and the point, or *ok = 0 (PointGeneratorError::InvalidPoint; out = identity encoding) */
+int32_t vkzg_ipa_crs_generate_at(vkzg_ctx* ctx, const uint8_t* seed, uint64_t seed_len, uint64_t index, vkzg_g1_affine* out,
+                                 int32_t* ok);
+
 /* ---- several GPUs of one box behind the same boundary ------------------------------------------------
  * A group owns one vkzg_ctx per device and one host thread per device per call; ONE host process (e.g. the Rust caller of
  * the vector-commit traits) drives the box.  Width-N keys are replicated on every device and batches are cut into

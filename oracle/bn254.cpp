@@ -58,6 +58,38 @@ void g1_affine_serialize_compressed(const G1Affine& a, uint8_t out[32]) {
     if (u256_cmp(yc, Fq::P().half) > 0) out[31] |= 0x80;
 }
 
+bool g1_affine_from_random_bytes(const uint8_t bytes[32], G1Affine& out) {
+    uint8_t b[32];
+    memcpy(b, bytes, 32);
+    const uint8_t flags = b[31] & 0xC0;
+    b[31] &= 0x3F;
+    U256 xc;
+    memcpy(xc.l, b, 32);
+    if (u256_cmp(xc, Fq::P().p) >= 0) return false;  // deserialize_compressed of the masked bytes fails
+    if (flags == 0xC0) return false;                 // SWFlags::from_u8: both bits set is invalid
+    if (flags == 0x40) {                             // infinity flag
+        if (!u256_is_zero(xc)) return false;
+        out.infinity = true;
+        out.x = Fq::zero();
+        out.y = Fq::zero();
+        return true;
+    }
+    Fq x = Fq::from_canonical(xc);
+    Fq rhs = x.sqr() * x + Fq::from_u64(3);
+    // p = 3 mod 4: the candidate root is rhs^((p+1)/4)
+    U256 e, one = {{1, 0, 0, 0}};
+    u256_add(e, Fq::P().p, one);
+    for (int i = 0; i < 4; ++i) e.l[i] = (e.l[i] >> 2) | (i < 3 ? (e.l[i + 1] << 62) : 0);
+    Fq y = rhs.pow(e);
+    if (!(y.sqr() == rhs)) return false;
+    const bool y_is_larger = u256_cmp(y.to_canonical(), Fq::P().half) > 0;
+    const bool want_larger = flags == 0x80;  // the encoder sets bit 7 for the larger root
+    out.infinity = false;
+    out.x = x;
+    out.y = (y_is_larger == want_larger) ? y : y.neg();
+    return true;
+}
+
 void g1_serialize_compressed(const G1& p, uint8_t out[32]) { g1_affine_serialize_compressed(p.to_affine(), out); }
 
 // ---------------------------------------------------------------- SHA-256

@@ -349,6 +349,13 @@ bool g1_on_curve(const G1Affine& a);
 //   |= 0x40 for the point at infinity (x = 0).          [UNVERIFIED-HERE: arkworks not on disk]
 void g1_serialize_compressed(const G1& p, uint8_t out[32]);
 void g1_affine_serialize_compressed(const G1Affine& a, uint8_t out[32]);
+// ark-ec 0.4 `Affine::from_random_bytes` (short Weierstrass) on 32 bytes, as EthereumHashToCurve calls it
+// (ipa/ipa_point_generator.rs:103-104): Fq::from_random_bytes_with_flags::<SWFlags> takes the two top bits of byte 31 as
+// flags, masks them off and rejects x >= p; flags 11 -> None; infinity flag -> identity iff x == 0, else None; otherwise
+// y = sqrt(x^3 + 3) (None for a non-residue) and the flag picks between y and -y by the SAME convention as the compressed
+// encoding above (bit 7 set <=> the y that serialises with bit 7), so from_random_bytes(serialize(P)) == P.  No subgroup
+// check (cofactor 1).  Returns false for None.                       [UNVERIFIED-HERE: same constant as the encoder]
+bool g1_affine_from_random_bytes(const uint8_t bytes[32], G1Affine& out);
 
 // ----------------------------------------------------------------------------------
 // SHA-256 (FIPS 180-4) and the ark-ff 0.4 DefaultFieldHasher<Sha256, 128>

@@ -372,6 +372,27 @@ int orc_ipa_verify_commitment(const uint8_t* bases, uint64_t N, const uint8_t* c
     }
 }
 
+// ------------------------------------------------------------------ IPA CRS (ipa_point_generator.rs:51-109)
+int orc_ipa_crs_gen(const uint8_t* seed, uint64_t seed_len, uint64_t num, uint8_t* out /* num points */, uint64_t* next_index) {
+    ORC_TRY
+    std::vector<G1Affine> v = ipa_crs_gen(std::vector<uint8_t>(seed, seed + seed_len), num, next_index);
+    for (size_t i = 0; i < v.size(); ++i) store_aff(out + 64 * i, v[i]);
+    ORC_CATCH
+}
+// gen_at: 1 = a point (written to out), 0 = PointGeneratorError::InvalidPoint
+int orc_ipa_crs_gen_at(const uint8_t* seed, uint64_t seed_len, uint64_t index, uint8_t* out) {
+    try {
+        uint8_t le[8];
+        for (int k = 0; k < 8; ++k) le[k] = (uint8_t)(index >> (8 * k));
+        G1Affine pt;
+        if (!eth_hash_to_curve(std::vector<uint8_t>(seed, seed + seed_len), le, 8, pt)) return 0;
+        store_aff(out, pt);
+        return 1;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
 // ------------------------------------------------------------------ KZG (K3; K4 restated with the known tau)
 int orc_kzg_setup(uint64_t max_items, const uint8_t* tau, uint8_t* out_lagrange /* next_pow2(max_items) points */) {
     ORC_TRY

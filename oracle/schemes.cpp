@@ -327,6 +327,30 @@ bool ipa_verify_commitment_proof(const IpaKey& key, const G1& commitment, const 
 }
 
 // ---------------------------------------------------------------------------------- kzg/mod.rs
+// ipa/ipa_point_generator.rs:97-109
+bool eth_hash_to_curve(const std::vector<uint8_t>& domain, const uint8_t* msg, size_t msg_len, G1Affine& out) {
+    std::vector<uint8_t> m(domain);
+    m.insert(m.end(), msg, msg + msg_len);
+    uint8_t h[32];
+    sha256(m.data(), m.size(), h);
+    return g1_affine_from_random_bytes(h, out);
+}
+
+// ipa/ipa_point_generator.rs:51-70
+std::vector<G1Affine> ipa_crs_gen(const std::vector<uint8_t>& seed, size_t num, uint64_t* next_index) {
+    std::vector<G1Affine> res;
+    uint64_t i = 0;
+    while (res.size() < num) {
+        uint8_t le[8];
+        for (int k = 0; k < 8; ++k) le[k] = (uint8_t)(i >> (8 * k));
+        G1Affine pt;
+        if (eth_hash_to_curve(seed, le, 8, pt)) res.push_back(pt);
+        ++i;
+    }
+    if (next_index) *next_index = i;
+    return res;
+}
+
 KzgKey kzg_setup(size_t max_items, const Fr& tau) {
     // gen(max_items): [G * tau^i]  (kzg_point_generator.rs:32-43), then domain.ifft (kzg/mod.rs:119-123):
     // out_j = (1/n) sum_i (tau^i G) w^{-ij}  ==  G * L_j(tau), over the padded domain of size n.

@@ -137,6 +137,13 @@ KzgMultiproof kzg_prove_multiproof(const KzgKey& key, const std::vector<ProverQu
 bool ipa_verify_multiproof(const IpaKey& key, const std::vector<VerifierQuery>& q, const IpaMultiproof& proof);
 bool kzg_verify_multiproof_with_tau(const KzgKey& key, const std::vector<VerifierQuery>& q, const KzgMultiproof& proof);
 
+// ---- ipa/ipa_point_generator.rs ---------------------------------------------------------------
+// EthereumHashToCurve::hash (:97-109): SHA-256(domain || message) -> Affine::from_random_bytes.
+bool eth_hash_to_curve(const std::vector<uint8_t>& domain, const uint8_t* msg, size_t msg_len, G1Affine& out);
+// IPAPointGenerator::gen (:51-70): the first `num` indices i = 0, 1, 2 ... (as usize -> 8 LE bytes) that hash to a point;
+// *next_index (optional) = the first index not consumed.  The caller checks num <= max (OutOfBounds).
+std::vector<G1Affine> ipa_crs_gen(const std::vector<uint8_t>& seed, size_t num, uint64_t* next_index);
+
 // ---- verkle-tree/src/node.rs ----------------------------------------------------------------
 // Node::gen_commitment (node.rs:212-277) on a tree built from (key, value) pairs with
 // Node::insert (node.rs:133-197).  `ext_width` is the const generic N used for the extension

@@ -378,6 +378,23 @@ def ipa_verify_commitment(bases, N, commitment, L, R, tip):
     return rc == 1
 
 
+def ipa_crs_gen(seed, num):
+    """IPAPointGenerator::gen -> (points [num,64], next unused index)"""
+    seed = bytes(seed)
+    out = np.zeros((num, 64), dtype=np.uint8)
+    nxt = ctypes.c_uint64(0)
+    assert lib().orc_ipa_crs_gen(ctypes.c_char_p(seed), ctypes.c_uint64(len(seed)), ctypes.c_uint64(num), _p(out), ctypes.byref(nxt)) == 0
+    return out, nxt.value
+
+
+def ipa_crs_gen_at(seed, index):
+    seed = bytes(seed)
+    out = np.zeros(64, dtype=np.uint8)
+    rc = lib().orc_ipa_crs_gen_at(ctypes.c_char_p(seed), ctypes.c_uint64(len(seed)), ctypes.c_uint64(index), _p(out))
+    assert rc >= 0
+    return out if rc == 1 else None
+
+
 def kzg_setup(max_items, tau):
     n = 1
     while n < max_items:

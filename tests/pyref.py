@@ -93,6 +93,35 @@ def ser_g1(a):
     return bytes(b)
 
 
+def from_random_bytes(b):
+    """ark-ec 0.4 Affine::from_random_bytes on 32 bytes (same flag convention as ser_g1): point, None-identity
+    is returned as the string "inf", rejection as False."""
+    flags = b[31] & 0xC0
+    x = int.from_bytes(bytes(b[:31]) + bytes([b[31] & 0x3F]), "little")
+    if x >= P_MOD or flags == 0xC0:
+        return False
+    if flags == 0x40:
+        return "inf" if x == 0 else False
+    rhs = (x * x * x + 3) % P_MOD
+    y = pow(rhs, (P_MOD + 1) // 4, P_MOD)
+    if y * y % P_MOD != rhs:
+        return False
+    larger = max(y, P_MOD - y)
+    return (x, larger if flags == 0x80 else P_MOD - larger)
+
+
+def ipa_crs_gen(seed, num):
+    """ipa_point_generator.rs:51-70 with EthereumHashToCurve (:97-109)"""
+    import hashlib
+    res, i = [], 0
+    while len(res) < num:
+        pt = from_random_bytes(hashlib.sha256(bytes(seed) + i.to_bytes(8, "little")).digest())
+        if pt is not False:
+            res.append(None if pt == "inf" else pt)
+        i += 1
+    return res, i
+
+
 def to_data_item(a):
     """lib.rs:56-67."""
     if a is None:

@@ -108,6 +108,9 @@ class OracleImpl:
     def tree_root(self, srs, keys, vals, ext_width):
         return orc.tree_commit(srs, keys, vals, ext_width=ext_width)
 
+    def ipa_crs(self, seed, num):
+        return orc.ipa_crs_gen(seed, num)[0]
+
 
 class LibImpl:
     """libvkzg through the C ABI (GPU)"""
@@ -146,6 +149,9 @@ class LibImpl:
             return L[0], R[0], tip[0]
         finally:
             k.free()
+
+    def ipa_crs(self, seed, num):
+        return self.eng.ipa_crs_generate(seed, num)[0]
 
     def kzg_setup(self, m, tau):
         g = orc.g1_generator()

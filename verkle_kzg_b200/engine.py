@@ -411,6 +411,25 @@ class Engine:
               "vkzg_kzg_powers")
         return out
 
+    # ---------------------------------------------------------------- IPA CRS generation (next row 8f-4)
+    def ipa_crs_generate(self, seed, num):
+        """IPAPointGenerator::gen (ipa_point_generator.rs:51-70): (points [num,64], next unused index)"""
+        seed = bytes(seed)
+        out = np.zeros((num, 64), dtype=np.uint8)
+        nxt = ctypes.c_uint64(0)
+        check(self._L.vkzg_ipa_crs_generate(self._ctx, ctypes.c_char_p(seed), ctypes.c_uint64(len(seed)), ctypes.c_uint64(num), hptr(out),
+                                            ctypes.byref(nxt)), "vkzg_ipa_crs_generate")
+        return out, nxt.value
+
+    def ipa_crs_generate_at(self, seed, index):
+        """IPAPointGenerator::gen_at (:72-81): the point, or None (InvalidPoint)"""
+        seed = bytes(seed)
+        out = np.zeros(64, dtype=np.uint8)
+        ok = ctypes.c_int32(0)
+        check(self._L.vkzg_ipa_crs_generate_at(self._ctx, ctypes.c_char_p(seed), ctypes.c_uint64(len(seed)), ctypes.c_uint64(index),
+                                               hptr(out), ctypes.byref(ok)), "vkzg_ipa_crs_generate_at")
+        return out if ok.value else None
+
     # ---------------------------------------------------------------- probes
     def probe_imad(self, kind, blocks, threads, iters):
         macs = ctypes.c_uint64(0)

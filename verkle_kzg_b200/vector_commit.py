@@ -33,6 +33,46 @@ class OutOfCRS(Exception):
     """KZGError::OutOfCRS / IPAError::OutOfCRS"""
 
 
+class OutOfBounds(Exception):
+    """PointGeneratorError::OutOfBounds (lib.rs:176-182)"""
+
+
+class InvalidPoint(Exception):
+    """PointGeneratorError::InvalidPoint"""
+
+
+class IPAPointGenerator:
+    """IPAPointGenerator<G, EthereumHashToCurve> (ipa/ipa_point_generator.rs:14-86): same constructor arguments,
+    defaults (max 256, seed "eth_verkle_oct_2021"), bounds checks and error cases; the hashing and the square roots
+    run on the GPU (vkzg_ipa_crs_generate)."""
+
+    def __init__(self, engine, max=256, seed=b"eth_verkle_oct_2021"):
+        self.engine = engine
+        self.max = max
+        self.seed = bytes(seed)
+
+    def set_max(self, max):
+        self.max = max
+
+    def gen(self, num):
+        if num > self.max:
+            raise OutOfBounds()
+        if num == 0:
+            return np.zeros((0, 64), dtype=np.uint8)
+        return self.engine.ipa_crs_generate(self.seed, num)[0]
+
+    def gen_at(self, index):
+        if index > self.max:  # the reference's own (inclusive) bound, ipa_point_generator.rs:73
+            raise OutOfBounds()
+        p = self.engine.ipa_crs_generate_at(self.seed, index)
+        if p is None:
+            raise InvalidPoint()
+        return p
+
+    def secret(self):
+        return self.seed
+
+
 class LagrangeBasis:
     """VCData impl of the reference (lagrange_basis.rs:151-178)"""
 
