@@ -254,6 +254,10 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* tree, vkzg_g
  * (`domain.ifft(&g1_points)`, inputs beyond m are the identity).                                                  */
 int32_t vkzg_kzg_setup(vkzg_ctx* ctx, const vkzg_g1_affine* powers, uint32_t m, vkzg_g1_affine* lagrange);
 int32_t vkzg_kzg_setup_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_powers, uint32_t m, vkzg_g1_affine* d_lagrange);
+/* KZG::setup(max_items = m, gen) when the generator's secret tau is known to the caller (kzg/mod.rs:115-124 reads
+ * gen.secret() itself): the same n = next_pow2(m) Lagrange points as vkzg_kzg_powers followed by vkzg_kzg_setup — canonical
+ * affine, bit-identical — computed as n closed-form scalars times G (key_id = a window key whose base 0 is G).        */
+int32_t vkzg_kzg_setup_from_secret(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* tau, uint32_t m, vkzg_g1_affine* lagrange);
 /* KZGRandomPointGenerator::gen (kzg_point_generator.rs:32-43): out[i] = tau^i * G, i < m; key_id = a window key whose
  * base 0 is the generator G                                                                                       */
 int32_t vkzg_kzg_powers(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* tau, uint32_t m, vkzg_g1_affine* out);

@@ -72,6 +72,29 @@ extern "C" {
                                             l: *const vkzg_g1_affine, r: *const vkzg_g1_affine, tip: *const vkzg_fr, ok: *mut i32) -> i32;
     pub fn vkzg_tree_path_to_stem(tree: *const Opaque, stem: *const u8, path_len: *mut u32, node_ids: *mut u32, units: *mut u8,
                                   commitments: *mut vkzg_g1_affine, clean: *mut u8) -> i32;
+    pub fn vkzg_multiproof_prove_batch(ctx: *mut vkzg_ctx, key_id: u32, scheme: i32, f: *const vkzg_fr, c: *const vkzg_g1_affine,
+                                       z: *const u64, y: *const vkzg_fr, m_each: *const u64, k: u64, d: *mut vkzg_g1_affine,
+                                       l: *mut vkzg_g1_affine, r: *mut vkzg_g1_affine, tip: *mut vkzg_fr, yout: *mut vkzg_fr) -> i32;
+    // setup code on the device
+    pub fn vkzg_kzg_powers(ctx: *mut vkzg_ctx, key_id: u32, tau: *const vkzg_fr, m: u32, out: *mut vkzg_g1_affine) -> i32;
+    pub fn vkzg_kzg_setup_from_secret(ctx: *mut vkzg_ctx, key_id: u32, tau: *const vkzg_fr, m: u32, lagrange: *mut vkzg_g1_affine) -> i32;
+    pub fn vkzg_ipa_crs_generate(ctx: *mut vkzg_ctx, seed: *const u8, seed_len: u64, num: u64, out: *mut vkzg_g1_affine,
+                                 next_index: *mut u64) -> i32;
+    pub fn vkzg_ipa_crs_generate_at(ctx: *mut vkzg_ctx, seed: *const u8, seed_len: u64, index: u64, out: *mut vkzg_g1_affine,
+                                    ok: *mut i32) -> i32;
+    // several GPUs of one box behind the same boundary (one host process)
+    pub fn vkzg_mgpu_create(out: *mut *mut Opaque, device_ids: *const i32, ngpu: u32) -> i32;
+    pub fn vkzg_mgpu_destroy(mg: *mut Opaque) -> i32;
+    pub fn vkzg_mgpu_size(mg: *const Opaque) -> u32;
+    pub fn vkzg_mgpu_ctx(mg: *mut Opaque, i: u32) -> *mut vkzg_ctx;
+    pub fn vkzg_mgpu_key_load(mg: *mut Opaque, bases: *const vkzg_g1_affine, n: u32, q: *const vkzg_g1_affine, kind: u32,
+                              window_bits: u32, key_id: *mut u32) -> i32;
+    pub fn vkzg_mgpu_key_free(mg: *mut Opaque, key_id: u32) -> i32;
+    pub fn vkzg_mgpu_msm(mg: *mut Opaque, key_id: u32, scalars: *const vkzg_fr, n: u64, out: *mut vkzg_g1_affine) -> i32;
+    pub fn vkzg_mgpu_commit_batch(mg: *mut Opaque, key_id: u32, scalars: *const vkzg_fr, w: u32, b: u64, out: *mut vkzg_g1_affine) -> i32;
+    pub fn vkzg_mgpu_ipa_commit_prove_batch(mg: *mut Opaque, key_id: u32, a: *const vkzg_fr, points: *const vkzg_fr, b: u64,
+                                            commitments: *mut vkzg_g1_affine, l: *mut vkzg_g1_affine, r: *mut vkzg_g1_affine,
+                                            tip: *mut vkzg_fr, y: *mut vkzg_fr) -> i32;
 }
 
 pub type Opaque = c_void;

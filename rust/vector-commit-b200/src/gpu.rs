@@ -327,3 +327,119 @@ impl GpuKzg {
         crate::kzg::KZG::<Bn254, H, D>::verify_point(&key.inner, commitment, point, proof, None)
     }
 }
+
+/// `IPAPointGenerator<G1Projective, EthereumHashToCurve>` (ipa/ipa_point_generator.rs:14-86) with the SHA-256
+/// try-and-increment and the square roots on the device (`vkzg_ipa_crs_generate`): same constructor, bounds and errors.
+pub struct GpuIpaPointGenerator {
+    max: usize,
+    seed: Vec<u8>,
+}
+impl GpuIpaPointGenerator {
+    pub fn new(max: usize, seed: Vec<u8>) -> Self {
+        Self { max, seed }
+    }
+    pub fn set_max(&mut self, max: usize) {
+        self.max = max;
+    }
+    fn with_ctx<T>(f: impl FnOnce(*mut vkzg_ctx) -> T) -> T {
+        let mut ctx = ptr::null_mut();
+        assert_eq!(unsafe { vkzg_ctx_create(&mut ctx, 0) }, 0, "no sm_100 GPU: libvkzg has no CPU fallback");
+        let r = f(ctx);
+        unsafe { vkzg_ctx_destroy(ctx) };
+        r
+    }
+}
+impl Default for GpuIpaPointGenerator {
+    fn default() -> Self {
+        Self { max: 256, seed: "eth_verkle_oct_2021".to_owned().into_bytes() } // ipa_point_generator.rs:38-47
+    }
+}
+impl crate::PointGenerator for GpuIpaPointGenerator {
+    type Point = G1Projective;
+    type Secret = Vec<u8>;
+
+    /// ipa_point_generator.rs:51-70
+    fn gen(&self, num: usize) -> Result<Vec<G1Projective>, crate::PointGeneratorError> {
+        if num > self.max {
+            return Err(crate::PointGeneratorError::OutOfBounds);
+        }
+        if num == 0 {
+            return Ok(vec![]);
+        }
+        let mut out = vec![vkzg_g1_affine::default(); num];
+        let st = Self::with_ctx(|ctx| unsafe {
+            vkzg_ipa_crs_generate(ctx, self.seed.as_ptr(), self.seed.len() as u64, num as u64, out.as_mut_ptr(), ptr::null_mut())
+        });
+        assert_eq!(st, 0);
+        Ok(out.iter().map(from_abi).collect())
+    }
+    /// ipa_point_generator.rs:72-81
+    fn gen_at(&self, index: usize) -> Result<G1Projective, crate::PointGeneratorError> {
+        if index > self.max {
+            return Err(crate::PointGeneratorError::OutOfBounds);
+        }
+        let mut out = vkzg_g1_affine::default();
+        let mut ok = 0i32;
+        let st = Self::with_ctx(|ctx| unsafe {
+            vkzg_ipa_crs_generate_at(ctx, self.seed.as_ptr(), self.seed.len() as u64, index as u64, &mut out, &mut ok)
+        });
+        assert_eq!(st, 0);
+        if ok == 1 { Ok(from_abi(&out)) } else { Err(crate::PointGeneratorError::InvalidPoint) }
+    }
+    fn secret(&self) -> Option<Vec<u8>> {
+        Some(self.seed.clone())
+    }
+}
+
+/// All GPUs of the box from ONE host process: `vkzg_mgpu_*` owns a context and a host thread per device.
+/// Width-N keys are replicated and a batch is cut into contiguous ranges (no exchange); an MSM key is point-range sharded
+/// and the 64-byte partial sums are added on device 0 after NVLink peer copies.
+pub struct GpuBox {
+    mg: *mut Opaque,
+}
+impl GpuBox {
+    /// `devices = &[]`: every visible GPU
+    pub fn new(devices: &[i32]) -> Self {
+        let mut mg = ptr::null_mut();
+        let st = unsafe { vkzg_mgpu_create(&mut mg, if devices.is_empty() { ptr::null() } else { devices.as_ptr() }, devices.len() as u32) };
+        assert_eq!(st, 0, "no sm_100 GPU: libvkzg has no CPU fallback");
+        GpuBox { mg }
+    }
+    pub fn gpus(&self) -> u32 {
+        unsafe { vkzg_mgpu_size(self.mg) }
+    }
+    pub fn load_window_key(&self, g: &[G1Projective], q: Option<&G1Projective>) -> u32 {
+        let bases: Vec<vkzg_g1_affine> = g.iter().map(to_abi).collect();
+        let qa = q.map(to_abi);
+        let mut id = 0u32;
+        let st = unsafe {
+            vkzg_mgpu_key_load(self.mg, bases.as_ptr(), bases.len() as u32, qa.as_ref().map_or(ptr::null(), |p| p as *const _), VKZG_KEY_WINDOW, 0, &mut id)
+        };
+        assert_eq!(st, 0);
+        id
+    }
+    pub fn load_msm_key(&self, g: &[G1Projective]) -> u32 {
+        let bases: Vec<vkzg_g1_affine> = g.iter().map(to_abi).collect();
+        let mut id = 0u32;
+        assert_eq!(unsafe { vkzg_mgpu_key_load(self.mg, bases.as_ptr(), bases.len() as u32, ptr::null(), VKZG_KEY_MSM, 0, &mut id) }, 0);
+        id
+    }
+    /// utils::inner_product (utils.rs:16-19) over all devices: KZG::commit at large n (configs[3])
+    pub fn msm(&self, key: u32, scalars: &[Fr]) -> G1Projective {
+        let mut out = vkzg_g1_affine::default();
+        assert_eq!(unsafe { vkzg_mgpu_msm(self.mg, key, fr_ptr(scalars), scalars.len() as u64, &mut out) }, 0);
+        from_abi(&out)
+    }
+    /// `rows.len() / width` independent commits spread over the devices
+    pub fn commit_many(&self, key: u32, rows: &[Fr], width: usize) -> Vec<G1Projective> {
+        let b = rows.len() / width;
+        let mut out = vec![vkzg_g1_affine::default(); b];
+        assert_eq!(unsafe { vkzg_mgpu_commit_batch(self.mg, key, fr_ptr(rows), width as u32, b as u64, out.as_mut_ptr()) }, 0);
+        out.iter().map(from_abi).collect()
+    }
+}
+impl Drop for GpuBox {
+    fn drop(&mut self) {
+        unsafe { vkzg_mgpu_destroy(self.mg) };
+    }
+}

@@ -163,4 +163,17 @@ def test_kzg_setup_group_ifft(eng, m):
     t2 = orc.rand_fr(np.random.default_rng(m), 1)[0]
     p2 = orc.g1_mul_gen_batch(orc.fr_to_buf([pow(t2, i, orc.R_MOD) for i in range(m)]))
     assert (eng.kzg_setup(p2) == orc.kzg_setup(m, t2)).all()
+    # the closed-form path (the generator's secret is known): the same canonical points
+    assert (eng.kzg_setup_from_secret(gkey, tau, m) == got).all()
+    assert (eng.kzg_setup_from_secret(gkey, orc.fr_to_buf([t2])[0], m) == orc.kzg_setup(m, t2)).all()
+    gkey.free()
+
+
+def test_kzg_setup_from_secret_edge_cases(eng):
+    """tau a domain element (tau w^-j = 1 for one j: the m/n branch), tau = 0 and tau = 1"""
+    gen = orc.g1_generator()
+    gkey = eng.load_key(gen.reshape(1, 64), window_bits=8)
+    w32 = orc.buf_to_fr(orc.domain_gen(32))[0]
+    for t, m in ((pow(w32, 5, orc.R_MOD), 20), (pow(w32, 5, orc.R_MOD), 32), (0, 9), (1, 16), (1, 11)):
+        assert (eng.kzg_setup_from_secret(gkey, orc.fr_to_buf([t])[0], m) == orc.kzg_setup(m, t)).all(), (t, m)
     gkey.free()

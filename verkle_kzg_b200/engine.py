@@ -405,6 +405,14 @@ class Engine:
         check(self._L.vkzg_kzg_setup(self._ctx, hptr(p), ctypes.c_uint32(len(p)), hptr(out)), "vkzg_kzg_setup")
         return out
 
+    def kzg_setup_from_secret(self, gen_key, tau, m):
+        """KZG::setup(m, KZGRandomPointGenerator::new(tau)) -> Lagrange SRS [next_pow2(m), 64]"""
+        n = 1 << _log2(m)
+        out = np.zeros((n, 64), dtype=np.uint8)
+        check(self._L.vkzg_kzg_setup_from_secret(self._ctx, ctypes.c_uint32(gen_key.id), hptr(u8(tau, 32).reshape(32)), ctypes.c_uint32(m),
+                                                 hptr(out)), "vkzg_kzg_setup_from_secret")
+        return out
+
     def kzg_powers(self, gen_key, tau, m):
         out = np.zeros((m, 64), dtype=np.uint8)
         check(self._L.vkzg_kzg_powers(self._ctx, ctypes.c_uint32(gen_key.id), hptr(u8(tau, 32).reshape(32)), ctypes.c_uint32(m), hptr(out)),
