@@ -33,6 +33,22 @@ int hc_field_op(int tag, int op, const uint8_t* a, const uint8_t* b, uint8_t* ou
     return 0;
 }
 
+// (a b + c d) R^-1 through the fused pair of products; inputs may be lazy (< 2p, or 2p itself); output canonicalised
+int hc_mul2(int tag, const uint8_t* a, const uint8_t* b, const uint8_t* c, const uint8_t* d, uint8_t* out, uint64_t n, int raw) {
+    for (uint64_t i = 0; i < n; ++i) {
+        fp_t r = tag == 0 ? fp_mul2_lazy<S>(ld(a + 32 * i), ld(b + 32 * i), ld(c + 32 * i), ld(d + 32 * i))
+                          : fp_mul2_lazy<Q>(ld(a + 32 * i), ld(b + 32 * i), ld(c + 32 * i), ld(d + 32 * i));
+        if (!raw) r = tag == 0 ? fp_canon<S>(r) : fp_canon<Q>(r);
+        st(out + 32 * i, r);
+    }
+    return 0;
+}
+// 2p - a
+int hc_neg_lazy(int tag, const uint8_t* a, uint8_t* out, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) st(out + 32 * i, tag == 0 ? fp_neg_lazy<S>(ld(a + 32 * i)) : fp_neg_lazy<Q>(ld(a + 32 * i)));
+    return 0;
+}
+
 // mode 0: madd(from_affine(a), b) ; 1: full add of two non-trivially scaled points ; 2: dbl(a) ; 3: a + b via madd into (a+b)-b
 int hc_g1_op(int mode, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     affine_t A = lda(a), B = lda(b);

@@ -85,6 +85,37 @@ def test_lazy_reduction_ops(hc, tag, mod):
     assert val(_op(hc, tag, 10, a, b)) == [(x + y) % mod for x, y in zip(xs, ys)]
 
 
+@pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
+def test_fused_pair_of_products(hc, tag, mod):
+    """fp_mul2_lazy: (a b + c d) / R in one interleaved Montgomery pass, operands anywhere in [0, 2p] (2p itself is what
+    fp_neg_lazy returns for 0); the raw result must respect the [0, 2p) invariant of the hot loops"""
+    rng = np.random.default_rng(500 + tag)
+    edge = [0, 1, mod - 1, mod, mod + 1, 2 * mod - 1, 2 * mod, (1 << 254) - 1, (1 << 254), mod + (1 << 253), 2 * mod - (1 << 32), (1 << 255) % (2 * mod)]
+    edge = [e for e in edge if e <= 2 * mod]
+    cols = []
+    for k in range(4):
+        v = [int.from_bytes(rng.bytes(32), "little") % (2 * mod + 1) for _ in range(500)]
+        v += edge[k:] + edge[:k] + [2 * mod] * 8 + [2 * mod - 1] * 4   # all-maximal rows: the worst case of the running total
+        cols.append(v)
+    raw = lambda v: np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in v), dtype=np.uint8).reshape(-1, 32).copy()
+    bufs = [raw(v) for v in cols]
+    rinv = pow(orc.MONT_R, -1, mod)
+    val = lambda buf: [int.from_bytes(bytes(r), "little") for r in buf]
+    want = [((a * b + c * d) * rinv) % mod for a, b, c, d in zip(*cols)]
+    for rawflag in (0, 1):
+        out = np.zeros_like(bufs[0])
+        hc.hc_mul2(tag, _p(bufs[0]), _p(bufs[1]), _p(bufs[2]), _p(bufs[3]), _p(out), ctypes.c_uint64(len(out)), rawflag)
+        got = val(out)
+        if rawflag:
+            assert all(g < 2 * mod for g in got)
+            got = [g % mod for g in got]
+        assert got == want
+    neg = np.zeros_like(bufs[0])
+    xs = [x for x in cols[0] if x < 2 * mod]
+    hc.hc_neg_lazy(tag, _p(raw(xs)), _p(neg), ctypes.c_uint64(len(xs)))
+    assert val(neg[:len(xs)]) == [2 * mod - x for x in xs]
+
+
 def test_group_ops(hc):
     rng = np.random.default_rng(7)
     ks = orc.rand_fr(rng, 6) + [1, 2]

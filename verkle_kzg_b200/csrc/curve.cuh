@@ -112,8 +112,10 @@ VK_HD void xyzz_madd(xyzz_t& acc, const affine_t& p) {
 // inlined code, i.e. it stays inside the instruction caches (ncu showed "no instruction" stalls otherwise).
 #ifdef __CUDA_ARCH__
 #define VK_MUL_HOT(a, b) fp_mul_lazy_ni<Q>(a, b)  // (fully inlined was measured slower: 164 k vs 173 k proofs/s)
+#define VK_MUL2_HOT(a, b, c, d) fp_mul2_lazy_ni<Q>(a, b, c, d)
 #else
 #define VK_MUL_HOT(a, b) fp_mul_lazy<Q>(a, b)
+#define VK_MUL2_HOT(a, b, c, d) fp_mul2_lazy<Q>(a, b, c, d)
 #endif
 // The accumulator coordinates are kept in [0, 2p) ("almost Montgomery": no final conditional subtraction in the ten
 // products); xyzz_canon() brings them back to [0, p) once, after the loop.  The table point is canonical.
@@ -138,7 +140,8 @@ __host__ __device__ __forceinline__ void xyzz_madd_hot(xyzz_t& acc, const affine
     fp_t PPP = VK_MUL_HOT(P, PP);
     fp_t Qv = VK_MUL_HOT(acc.x, PP);
     fp_t X3 = fp_sub_lazy<Q>(fp_sub_lazy<Q>(VK_MUL_HOT(R, R), PPP), fp_add_lazy<Q>(Qv, Qv));
-    fp_t Y3 = fp_sub_lazy<Q>(VK_MUL_HOT(R, fp_sub_lazy<Q>(Qv, X3)), VK_MUL_HOT(acc.y, PPP));
+    // Y3 = R (Q - X3) - Y1 PPP as ONE fused pair of products sharing their Montgomery reduction (200 instead of 272 MACs)
+    fp_t Y3 = VK_MUL2_HOT(R, fp_sub_lazy<Q>(Qv, X3), fp_neg_lazy<Q>(acc.y), PPP);
     acc.x = X3;
     acc.y = Y3;
     acc.zz = VK_MUL_HOT(acc.zz, PP);

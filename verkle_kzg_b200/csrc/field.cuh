@@ -328,6 +328,78 @@ template <class P>
 __host__ __device__ __noinline__ fp_t fp_mul_lazy_ni(const fp_t a, const fp_t b) {
     return fp_mul_lazy<P>(a, b);
 }
+// Fused pair of products for the hot loops:  (a b + c d) R^-1 mod p  in ONE interleaved pass — the two row products of a
+// step share its reduction row, 8 x (8 + 8 + 8 + 1) = 200 multiply-accumulates instead of the 272 of two separate products
+// (Y3 = R (Q - X3) + (-Y1) PPP of the mixed addition).  Inputs in [0, 2p]; the running total stays below 5p (1 + 2^-32)
+// < 2^256 after every shift and below 2^288 inside a row, so neither array can carry out of its top limb beyond what
+// `top` catches; the result (a b + c d + M p) / R < 8 p^2 / R + p < 2.51 p is brought back to [0, 2p) by one conditional
+// subtraction of 2p.
+template <class P>
+VK_HD fp_t fp_mul2_lazy(const fp_t& a, const fp_t& b, const fp_t& c, const fp_t& d) {
+    uint32_t u[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        uint64_t t0 = (uint64_t)a.l[j] * b.l[0];
+        uint64_t t1 = (uint64_t)a.l[j + 1] * b.l[0];
+        u[j] = (uint32_t)t0;
+        u[j + 1] = (uint32_t)(t0 >> 32);
+        v[j] = (uint32_t)t1;
+        v[j + 1] = (uint32_t)(t1 >> 32);
+    }
+    mad_row4_nc(v, c.l[1], c.l[3], c.l[5], c.l[7], d.l[0]);
+    mad_row4(u, v[7], c.l[0], c.l[2], c.l[4], c.l[6], d.l[0]);
+    reduce_step<P>(u, v);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        {
+            uint32_t y[8];
+            shift_mad_row4(v[0], y, u, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+            mad_row4(v, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+            mad_row4_nc(y, c.l[1], c.l[3], c.l[5], c.l[7], d.l[i]);
+            mad_row4(v, y[7], c.l[0], c.l[2], c.l[4], c.l[6], d.l[i]);
+            reduce_step<P>(v, y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = y[k];
+        }
+        if (i + 1 < 8) {
+            uint32_t y[8];
+            shift_mad_row4(u[0], y, v, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i + 1]);
+            mad_row4(u, y[7], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i + 1]);
+            mad_row4_nc(y, c.l[1], c.l[3], c.l[5], c.l[7], d.l[i + 1]);
+            mad_row4(u, y[7], c.l[0], c.l[2], c.l[4], c.l[6], d.l[i + 1]);
+            reduce_step<P>(u, y);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = y[k];
+        }
+    }
+    uint32_t vs[8];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) vs[k] = v[k + 1];
+    vs[7] = 0;
+    fp_t r;
+    add8(r.l, u, vs);
+    uint32_t dd[8], p2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p2[k] = (P::p(k) << 1) | (k ? P::p(k - 1) >> 31 : 0);
+    uint32_t borrow = sub8(dd, r.l, p2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = borrow ? r.l[k] : dd[k];
+    return r;
+}
+template <class P>
+__host__ __device__ __noinline__ fp_t fp_mul2_lazy_ni(const fp_t a, const fp_t b, const fp_t c, const fp_t d) {
+    return fp_mul2_lazy<P>(a, b, c, d);
+}
+// 2p - a for a in [0, 2p): the negation of a lazy value, in (0, 2p]
+template <class P>
+VK_HD fp_t fp_neg_lazy(const fp_t& a) {
+    uint32_t p2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p2[k] = (P::p(k) << 1) | (k ? P::p(k - 1) >> 31 : 0);
+    fp_t r;
+    sub8(r.l, p2, a.l);
+    return r;
+}
 // lazy add / sub / double on [0, 2p)
 template <class P>
 VK_HD fp_t fp_sub_lazy(const fp_t& a, const fp_t& b) {
