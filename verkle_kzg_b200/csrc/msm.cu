@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restric
 // operations, most of them doublings or pair-split additions, against the ~52 full additions of the running-sum form
 // (measured at n = 2^16: 325 -> see profiles/ us for the two kernels).
 // ---------------------------------------------------------------------------------------------------------------
-static const int BS_THREADS = 256;
-static const int BS_SLICE = 2048;  // buckets per CTA
+static const int BS_THREADS = 128;
+static const int BS_SLICE = 512;   // buckets per CTA (4 warps: one per sub-partition, so the dependent additions do not share a multiplier pipe)
 
 __global__ void __launch_bounds__(BS_THREADS) k_msm_bitsums(const xyzz_t* __restrict__ buckets, uint32_t nb, uint32_t slices,
                                                             xyzz_t* __restrict__ out /*[bits][slices]*/) {
@@ -213,29 +213,48 @@ __global__ void __launch_bounds__(BS_THREADS) k_msm_bitsums(const xyzz_t* __rest
     }
 }
 
-// one CTA, warp j <-> bit j (bits <= 32 warps): fold the slice sums (lanes), 2^j by j doublings, sum over the warps
-__global__ void __launch_bounds__(1024) k_msm_bitcombine(const xyzz_t* __restrict__ part, uint32_t bits, uint32_t slices,
-                                                         xyzz_t* __restrict__ out) {
-    __shared__ xyzz_t sh[32];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// one WARP-sized CTA per bit j (each on its own SM: the chains below are dependent point operations, and warps of one CTA
+// would share a multiplier pipe): fold the slice sums of bit j (lanes), then 2^j by j doublings with the products of a
+// doubling spread over the four lanes of a quad.  The last CTA to finish (ticket) adds the c values with a shuffle tree.
+// (measured at n = 2^16, c = 13: 124 us as one 13-warp CTA -> 76 us; k_msm_bitsums 108 -> 52 us with 512-bucket slices)
+__global__ void __launch_bounds__(32) k_msm_bitcombine(const xyzz_t* __restrict__ part, uint32_t bits, uint32_t slices,
+                                                       xyzz_t* __restrict__ scaled /*[bits]*/, uint32_t* __restrict__ ticket,
+                                                       xyzz_t* __restrict__ out) {
+    const uint32_t bit = blockIdx.x, lane = threadIdx.x;
     xyzz_t v = xyzz_inf();
-    if (warp < bits)
-        for (uint32_t sidx = lane; sidx < slices; sidx += 32) v = xyzz_add_ni(v, part[warp * slices + sidx]);
-    uint32_t span = slices < 32 ? slices : 32;
+    for (uint32_t sidx = lane; sidx < slices; sidx += 32) v = xyzz_add_ni(v, part[bit * slices + sidx]);
+    const uint32_t span = slices < 32 ? slices : 32;
 #pragma unroll 1
     for (uint32_t off = 1; off < span; off <<= 1) v = xyzz_add_pair(v, (int)off);
+    // every lane continues with lane 0's sum (the quad form needs whole warps; the quads compute the same value)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v.x.l[i] = __shfl_sync(0xffffffffu, v.x.l[i], 0);
+        v.y.l[i] = __shfl_sync(0xffffffffu, v.y.l[i], 0);
+        v.zz.l[i] = __shfl_sync(0xffffffffu, v.zz.l[i], 0);
+        v.zzz.l[i] = __shfl_sync(0xffffffffu, v.zzz.l[i], 0);
+    }
+#pragma unroll 1
+    for (uint32_t j = 0; j < bit; ++j) v = xyzz_dbl_quad(v);
+    uint32_t last = 0;
     if (lane == 0) {
-#pragma unroll 1
-        for (uint32_t j = 0; j < warp && warp < bits; ++j) v = xyzz_dbl_ni(v);
-        sh[warp] = warp < bits ? v : xyzz_inf();
+        scaled[bit] = v;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == bits - 1 ? 1u : 0u;
     }
-    __syncthreads();
-    if (warp == 0) {
-        xyzz_t t = lane < bits ? sh[lane] : xyzz_inf();
-#pragma unroll 1
-        for (int off = 1; off < 32; off <<= 1) t = xyzz_add_pair(t, off);
-        if (lane == 0) out[0] = t;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    xyzz_t t = xyzz_inf();
+    if (lane < bits) {
+        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(scaled + lane);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i] = src[i];
     }
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) t = xyzz_add_pair(t, off);
+    if (lane == 0) out[0] = t;
 }
 
 // ---- running-sum form of the weighted bucket sum: less work (2 additions per bucket), longer chain — used for large bucket
@@ -302,9 +321,9 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     DevBuf<uint32_t> counts, offsets, entries;
     DevBuf<xyzz_t> buckets, partial;
     cudaStream_t s = ctx->stream;
-    VK_TRY(counts.alloc(ctx, nb + 1));
+    VK_TRY(counts.alloc(ctx, nb + 2));  // [nb] = dropped entries of the optimistic scatter, [nb + 1] = bit-combine ticket
     VK_TRY(buckets.alloc(ctx, nb));
-    VK_CUDA(cudaMemsetAsync(counts, 0, (nb + 1) * sizeof(uint32_t), s));
+    VK_CUDA(cudaMemsetAsync(counts, 0, (nb + 2) * sizeof(uint32_t), s));
     uint32_t gb = ceil_div_u64(n, 256);
     // lanes per bucket: aim at ~32 additions per lane
     uint64_t avg = (uint64_t)n * k.W / nb;
@@ -315,6 +334,9 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         p_env = e ? atoi(e) : 0;
     }
     while (P < 32 && avg / (P * 2) >= 48) P *= 2;  // ~64 additions per lane (measured best on B200: P = 8 at n = 2^20)
+    // (the top window is short — 7 bits at c = 13 — so the first ~100 buckets also receive n / 2^7 top digits each, 4x the mean
+    //  list: with P = 32 their lanes still finish inside the kernel's throughput-bound time; striping those lists over extra
+    //  lane groups was measured: it rescues P = 8 / 16 (1.03 -> 0.63 ms at 2^16) but the best configuration stays P = 32.)
     // small slices: one lane per bucket leaves most of the GPU idle (2^16 points: 32 K lanes of ~32 dependent additions on
     // 75 K thread slots) — split the buckets further until the grid fills about two waves, down to ~6 additions per lane
     while (P < 32 && (uint64_t)nb * P < (uint64_t)ctx->sm_count * 512 * 2 && avg / (P * 2) >= 6) P *= 2;
@@ -378,10 +400,10 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         // measured at n = 2^16 (B200): c = 16 / running sums 325 us for this tail; c = 13 / bit-parallel see DESIGN.md
         const uint32_t bits = k.c, slices = (nb + BS_SLICE - 1) / BS_SLICE;  // weights 1 .. 2^(c-1): c bits
         rblocks = bits * slices;
-        VK_TRY(partial.alloc(ctx, (size_t)rblocks + 1));
+        VK_TRY(partial.alloc(ctx, (size_t)rblocks + 1 + bits));
         k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(buckets, nb, slices, partial);
         VK_TRY(launch_check(ctx));
-        k_msm_bitcombine<<<1, 32 * bits, 0, s>>>(partial, bits, slices, partial.p + rblocks);
+        k_msm_bitcombine<<<bits, 32, 0, s>>>(partial, bits, slices, partial.p + rblocks + 1, counts.p + nb + 1, partial.p + rblocks);
         VK_TRY(launch_check(ctx));
     } else {
         uint32_t segs = (nb + RED_SEG - 1) / RED_SEG;
