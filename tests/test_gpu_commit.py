@@ -131,6 +131,27 @@ def test_msm_matches_oracle(eng, n, c):
     key.free()
 
 
+@pytest.mark.parametrize("c", [5, 14, 15, 17, 19])
+def test_window_counts_at_the_top_of_the_scalar_range(eng, c):
+    """W = ceil(255 / c) digits (the scalars are < r < 2^254): widths whose last window is full (15, 17: c W = 255), nearly
+    empty (14: two bits) or odd; scalars that maximise the top digit and the carries into it — MSM keys and window keys"""
+    n = 600
+    bases = _bases(n, 700 + c)
+    edge = [orc.R_MOD - 1, orc.R_MOD - 2, (1 << 253), (1 << 253) - 1, (1 << 253) + (1 << 252), orc.R_MOD >> 1, (1 << (c - 1)), (1 << (c - 1)) - 1,
+            (1 << c) - 1, sum(1 << (c * w + c - 1) for w in range(255 // c) if c * w + c - 1 < 253), 0, 1]
+    rng = np.random.default_rng(c)
+    s = np.concatenate([orc.fr_to_buf(edge), orc.rand_fr_buf(rng, n - len(edge))])
+    exp = orc.msm(bases, s, mode="pippenger")
+    mk = eng.load_key(bases, kind=2, window_bits=c)
+    assert (eng.msm(mk, s) == exp).all()
+    mk.free()
+    if c <= 17:  # window key: 600 bases x W x 2^(c-1) entries
+        wk = eng.load_key(bases[:64], window_bits=c)
+        got = eng.commit_batch(wk, s[:64][None])
+        assert (got[0] == orc.msm(bases[:64], s[:64], mode="pippenger")).all()
+        wk.free()
+
+
 def test_msm_degenerate_scalars(eng):
     n = 4096
     bases = _bases(n, 99)

@@ -396,7 +396,12 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     }
     VK_TRY(launch_check(ctx));
     uint32_t rblocks;
-    if (nb <= 8192) {
+    static int bitpar_max = -1;
+    if (bitpar_max < 0) {
+        const char* e = getenv("VKZG_MSM_BITPAR_MAX");
+        bitpar_max = e ? atoi(e) : 16384;
+    }
+    if (nb <= (uint32_t)bitpar_max) {
         // measured at n = 2^16 (B200): c = 16 / running sums 325 us for this tail; c = 13 / bit-parallel see DESIGN.md
         const uint32_t bits = k.c, slices = (nb + BS_SLICE - 1) / BS_SLICE;  // weights 1 .. 2^(c-1): c bits
         rblocks = bits * slices;
