@@ -3,7 +3,7 @@
 // stalls" (VERDICT r1 item 3); the default stays the XYZZ kernel of commit.cu, which is faster on B200:
 //
 //     width-256 commits, batch 2^14, c = 20 (54.5 M table additions)      XYZZ 9.15 ms      batch-affine 10.35 ms
-//     streaming levels 7.0 M additions/ms, gather level 4.6 M/ms, XYZZ kernel 5.96 M/ms   (profiles/r02_batch_affine.md)
+//     streaming levels 7.0 M additions/ms, gather level 4.6 M/ms, XYZZ kernel 5.96 M/ms   
 //
 // Why it was tried: the multiplier — not occupancy, not memory — bounds these kernels (profiles/r02_mulbench4_occupancy.txt:
 // the 8 x 32-bit Montgomery product saturates at 67 G mul/s from two resident warps per sub-partition on), and an affine
