@@ -98,6 +98,8 @@ int32_t vkzg_ctx_destroy(vkzg_ctx* ctx) {
     for (auto st : ctx->side_streams) cudaStreamDestroy(st);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VKZG_OK;

@@ -319,12 +319,12 @@ int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const 
         return ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y, d_prefix_each,
                                     each_len);
     if (!ctx->aux_stream) VK_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_fork) VK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    if (!ctx->ev_join) VK_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     uint32_t rounds = 0;
     while ((1u << rounds) < N) ++rounds;
     const uint64_t B0 = B / 2, B1 = B - B0;
-    cudaEvent_t fork, join;
-    VK_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    VK_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    cudaEvent_t fork = ctx->ev_fork, join = ctx->ev_join;
     VK_CUDA(cudaEventRecord(fork, ctx->stream));          // inputs are ready in main-stream order
     VK_CUDA(cudaStreamWaitEvent(ctx->aux_stream, fork, 0));
     cudaStream_t main_stream = ctx->stream;
@@ -337,8 +337,6 @@ int32_t ipa_prove_core(vkzg_ctx* ctx, const Key& k, int mode, uint32_t N, const 
     int32_t st0 = ipa_prove_one_stream(ctx, k, mode, N, d_a, d_points, d_C, B0, prefix, prefix_len, dst, d_L, d_R, d_tip, d_y, d_prefix_each,
                                        each_len);
     cudaStreamWaitEvent(ctx->stream, join, 0);
-    cudaEventDestroy(fork);
-    cudaEventDestroy(join);
     return st0 != VKZG_OK ? st0 : st1;
 }
 

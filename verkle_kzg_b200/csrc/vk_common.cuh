@@ -71,6 +71,7 @@ struct vkzg_ctx {
     // every k_fixed_base_msm / k_msm_bucket launch on this context's stream
     cudaStream_t copy_stream = nullptr;  // host<->device staging of the batched host-pointer calls overlaps compute
     cudaStream_t aux_stream = nullptr;   // second compute stream: two half-batches of IPA proofs run interleaved
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // its fork / join events (created once with the stream)
     std::vector<cudaStream_t> side_streams;  // batched multiproofs: the per-proof row kernels of different proofs overlap
     bool ipa_two_streams = true;         // VKZG_OPT_IPA_TWO_STREAMS
     int batch_affine = -1;               // VKZG_OPT_BATCH_AFFINE: -1 automatic, 0 off, 1 on (big dense batches)
