@@ -25,7 +25,7 @@ def main():
     while time.time() - t0 < budget:
         it += 1
         N = int(rng.choice([2, 4, 8, 16, 32, 64, 256]))
-        c = int(rng.choice([4, 7, 8, 11, 13, 16]))
+        c = int(rng.choice([4, 5, 7, 8, 11, 13, 15, 16, 17] if N <= 64 else [4, 7, 8, 11, 13, 16]))
         k0, k1 = orc.rand_fr(rng, 2)
         bases = orc.points_walk(k0, k1, N + 1)
         key = eng.load_key(bases[:N], q=bases[N], window_bits=c)
@@ -105,9 +105,46 @@ def main():
                 assert (nt.commitment(eng, tree_key) == orc.tree_commit(tree_bases, keys, vals, ext_width=width)).all(), ("tree-b", kl, width, cut)
                 nt.close()
                 eng.set_option(eng.OPT_TREE_FLATTEN, 0)
-        # MSM
-        n = int(rng.integers(1, 3000))
-        cm = int(rng.choice([6, 9, 12, 16]))
+        # IPA commitment proofs (ipa/mod.rs:199-265) and the batched multiproof entry (K proofs, one call == K single calls)
+        if it % 3 == 0 and N >= 4:
+            key = eng.load_key(bases[:N], q=bases[N], window_bits=8)
+            Lc, Rc, tc = eng.ipa_prove_commitment_batch(key, a, C)
+            for i in range(Bp):
+                eL, eR, etip = orc.ipa_prove_commitment(bases, N, a[i], C[i])
+                assert (Lc[i] == eL).all() and (Rc[i] == eR).all() and (tc[i] == etip).all(), ("ipa-commitment", N)
+            assert eng.ipa_verify_commitment_batch(key, C, Lc, Rc, tc).all()
+            K = int(rng.integers(1, 5))
+            m_each = rng.integers(1, 12, K).astype(np.uint64)
+            mt = int(m_each.sum())
+            fb = orc.rand_fr_buf(rng, mt * N).reshape(mt, N, 32)
+            Cb = eng.commit_batch(key, fb)
+            zb2 = rng.integers(0, N, mt).astype(np.uint64)
+            yb2 = np.stack([fb[i, int(zb2[i])] for i in range(mt)])
+            outs = eng.multiproof_prove_batch(key, "ipa", fb, Cb, zb2, yb2, m_each)
+            off = 0
+            for kk_ in range(K):
+                me = int(m_each[kk_])
+                exp = orc.multiproof_prove("ipa", bases, N, fb[off:off + me], Cb[off:off + me], zb2[off:off + me], yb2[off:off + me])
+                assert all((outs[kk_][k] == exp[k]).all() for k in ("D", "L", "R", "tip", "y")), ("mpbatch", N, K, kk_)
+                off += me
+            key.free()
+        # setup paths: IPA CRS from a random seed, KZG Lagrange SRS from the secret and as the group FFT
+        if it % 5 == 0:
+            seed = rng.bytes(int(rng.integers(0, 130)))
+            num = int(rng.integers(1, 300))
+            got_crs, nxt = eng.ipa_crs_generate(seed, num)
+            exp_crs, exp_nxt = orc.ipa_crs_gen(seed, num)
+            assert (got_crs == exp_crs).all() and nxt == exp_nxt, ("crs", len(seed), num)
+            gk = eng.load_key(orc.g1_generator()[None], window_bits=8)
+            tau = orc.rand_fr(rng, 1)[0]
+            mset = int(rng.integers(1, 70))
+            lag = eng.kzg_setup_from_secret(gk, orc.fr_to_buf([tau])[0], mset)
+            assert (lag == orc.kzg_setup(mset, tau)).all(), ("kzg-setup-secret", mset)
+            assert (eng.kzg_setup(eng.kzg_powers(gk, orc.fr_to_buf([tau])[0], mset)) == lag).all(), ("kzg-setup-fft", mset)
+            gk.free()
+        # MSM (now and then large enough for the optimistic single-pass scatter and both weighted-sum forms)
+        n = int(rng.integers(1, 3000)) if it % 6 else int(rng.integers(4096, 40000))
+        cm = int(rng.choice([6, 9, 12, 16])) if it % 6 else int(rng.choice([0, 9, 13, 15, 16, 17]))
         mb = orc.points_walk(k1, k0, n)
         mk = eng.load_key(mb, kind=2, window_bits=cm)
         ms = orc.rand_fr_buf(rng, n)
