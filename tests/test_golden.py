@@ -8,6 +8,7 @@ import pytest
 import orc
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vectors.npz"))
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vectors_r2.npz"))  # make_golden_r2.py
 N = 32
 
 
@@ -25,6 +26,44 @@ def test_oracle_reproduces_golden():
         assert (v == G[f"mp_out_{k}"]).all(), k
     assert (orc.tree_commit(G["tree_bases"], G["tree_keys"], G["tree_vals"], ext_width=256) == G["tree_root_w256"]).all()
     assert (orc.to_data_item(bases[:8]) == G["to_data_item"]).all()
+
+
+def test_oracle_reproduces_round2_golden():
+    pts, nxt = orc.ipa_crs_gen(b"eth_verkle_oct_2021", 24)
+    assert (pts == G2["crs_default"]).all() and nxt == int(G2["crs_default_next"][0])
+    pts2, nxt2 = orc.ipa_crs_gen(bytes(range(70)), 9)
+    assert (pts2 == G2["crs_seed70"]).all() and nxt2 == int(G2["crs_seed70_next"][0])
+    L, R, tip = orc.ipa_prove_commitment(G2["cp_bases"], 16, G2["cp_a"], G2["cp_C"])
+    assert (L == G2["cp_L"]).all() and (R == G2["cp_R"]).all() and (tip == G2["cp_tip"]).all()
+    assert orc.ipa_verify_commitment(G2["cp_bases"], 16, G2["cp_C"], L, R, tip)
+    assert (orc.kzg_setup(20, orc.buf_to_fr(G2["setup_tau"][None])[0]) == G2["setup_m20"]).all()
+    k0, k1 = orc.buf_to_fr(G2["msm_k"])
+    assert (orc.msm(orc.points_walk(k0, k1, 3000), G2["msm_scalars"], mode="pippenger") == G2["msm_result"]).all()
+
+
+@pytest.mark.gpu
+def test_libvkzg_reproduces_round2_golden():
+    from verkle_kzg_b200 import Engine
+    eng = Engine(0)
+    pts, nxt = eng.ipa_crs_generate(b"eth_verkle_oct_2021", 24)
+    assert (pts == G2["crs_default"]).all() and nxt == int(G2["crs_default_next"][0])
+    pts2, nxt2 = eng.ipa_crs_generate(bytes(range(70)), 9)
+    assert (pts2 == G2["crs_seed70"]).all() and nxt2 == int(G2["crs_seed70_next"][0])
+    key = eng.load_key(G2["cp_bases"][:16], q=G2["cp_bases"][16], window_bits=8)
+    assert (eng.commit_batch(key, G2["cp_a"][None])[0] == G2["cp_C"]).all()
+    L, R, tip = eng.ipa_prove_commitment_batch(key, G2["cp_a"][None], G2["cp_C"][None])
+    assert (L[0] == G2["cp_L"]).all() and (R[0] == G2["cp_R"]).all() and (tip[0] == G2["cp_tip"]).all()
+    assert eng.ipa_verify_commitment_batch(key, G2["cp_C"][None], L, R, tip).all()
+    gk = eng.load_key(orc.g1_generator()[None], window_bits=8)
+    assert (eng.kzg_setup_from_secret(gk, G2["setup_tau"], 20) == G2["setup_m20"]).all()
+    assert (eng.kzg_setup(eng.kzg_powers(gk, G2["setup_tau"], 20)) == G2["setup_m20"]).all()
+    k0, k1 = orc.buf_to_fr(G2["msm_k"])
+    mb = orc.points_walk(k0, k1, 3000)
+    for c in (0, 9, 15, 17):
+        mk = eng.load_key(mb, kind=2, window_bits=c)
+        assert (eng.msm(mk, G2["msm_scalars"]) == G2["msm_result"]).all(), c
+        mk.free()
+    eng.close()
 
 
 @pytest.mark.gpu

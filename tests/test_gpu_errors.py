@@ -113,3 +113,43 @@ def test_key_load_validation_and_range_checks(eng):
     k8 = eng.load_key(bases[:8], window_bits=8)
     assert (eng.commit_batch(k8, s) == orc.commit_batch(bases[:8], s)).all()
     k8.free()
+
+
+def test_setup_entry_points_reject_bad_arguments(eng):
+    """vkzg_ipa_crs_generate[_at], vkzg_kzg_setup_from_secret, vkzg_kzg_powers: status codes, no crashes"""
+    from verkle_kzg_b200 import _lib
+    L = _lib.lib()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    out = np.zeros((4, 64), dtype=np.uint8)
+    nxt = ctypes.c_uint64(0)
+    ok = ctypes.c_int32(7)
+    seed = ctypes.c_char_p(b"seed")
+    # null output / zero count / null seed with a length / null ctx
+    assert L.vkzg_ipa_crs_generate(eng._ctx, seed, ctypes.c_uint64(4), ctypes.c_uint64(4), None, ctypes.byref(nxt)) == -2
+    assert L.vkzg_ipa_crs_generate(eng._ctx, seed, ctypes.c_uint64(4), ctypes.c_uint64(0), p(out), ctypes.byref(nxt)) == -2
+    assert L.vkzg_ipa_crs_generate(eng._ctx, None, ctypes.c_uint64(4), ctypes.c_uint64(4), p(out), ctypes.byref(nxt)) == -2
+    assert L.vkzg_ipa_crs_generate(None, seed, ctypes.c_uint64(4), ctypes.c_uint64(4), p(out), ctypes.byref(nxt)) == -2
+    assert L.vkzg_ipa_crs_generate(eng._ctx, seed, ctypes.c_uint64(4), ctypes.c_uint64((1 << 28) + 1), p(out), ctypes.byref(nxt)) == -3
+    # an empty seed is a valid seed (NULL pointer, length 0); next_index may be NULL
+    assert L.vkzg_ipa_crs_generate(eng._ctx, None, ctypes.c_uint64(0), ctypes.c_uint64(4), p(out), None) == 0
+    assert (out == orc.ipa_crs_gen(b"", 4)[0]).all()
+    assert L.vkzg_ipa_crs_generate_at(eng._ctx, seed, ctypes.c_uint64(4), ctypes.c_uint64(0), p(out), None) == -2
+    assert L.vkzg_ipa_crs_generate_at(eng._ctx, seed, ctypes.c_uint64(4), ctypes.c_uint64(0), None, ctypes.byref(ok)) == -2
+    # an index far beyond any `max` still answers (the bound is the caller's, PointGeneratorError::OutOfBounds)
+    assert L.vkzg_ipa_crs_generate_at(eng._ctx, seed, ctypes.c_uint64(4), ctypes.c_uint64((1 << 63) + 12345), p(out), ctypes.byref(ok)) == 0
+    ref = orc.ipa_crs_gen_at(b"seed", (1 << 63) + 12345)
+    assert (ok.value == 1) == (ref is not None) and (ref is None or (out[0] == ref).all())
+    # KZG setup from the secret: needs a window key whose base 0 is G, a secret, m >= 1
+    g = orc.g1_generator()
+    wkey = eng.load_key(g[None], window_bits=8)
+    mkey = eng.load_key(g[None], kind=2, window_bits=8)
+    tau = orc.fr_to_buf([5])[0]
+    lag = np.zeros((4, 64), dtype=np.uint8)
+    assert L.vkzg_kzg_setup_from_secret(eng._ctx, ctypes.c_uint32(mkey.id), p(tau), ctypes.c_uint32(4), p(lag)) == -2
+    assert L.vkzg_kzg_setup_from_secret(eng._ctx, ctypes.c_uint32(wkey.id), None, ctypes.c_uint32(4), p(lag)) == -2
+    assert L.vkzg_kzg_setup_from_secret(eng._ctx, ctypes.c_uint32(wkey.id), p(tau), ctypes.c_uint32(0), p(lag)) == -2
+    assert L.vkzg_kzg_setup_from_secret(eng._ctx, ctypes.c_uint32(wkey.id), p(tau), ctypes.c_uint32((1 << 24) + 1), p(lag)) == -3
+    assert L.vkzg_kzg_setup_from_secret(eng._ctx, ctypes.c_uint32(wkey.id), p(tau), ctypes.c_uint32(4), p(lag)) == 0
+    assert (lag == orc.kzg_setup(4, 5)).all()
+    wkey.free()
+    mkey.free()
