@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 
 #include "vk_common.cuh"
 
@@ -216,6 +217,30 @@ static fp_t fr_from_le_bytes(const uint8_t* b, size_t len) {
     return r;
 }
 
+// f(begin, end, part) over `parts` contiguous ranges of [0, n) on host threads (part 0 on the caller's)
+template <class F>
+static void parallel_ranges(size_t n, unsigned parts, F&& f) {
+    if (parts <= 1 || n < 4096) {
+        f((size_t)0, n, 0u);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(parts - 1);
+    for (unsigned p = 1; p < parts; ++p) th.emplace_back([&, p] { f(n * p / parts, n * (p + 1) / parts, p); });
+    f((size_t)0, n / parts, 0u);
+    for (auto& x : th) x.join();
+}
+static unsigned host_parts() {
+    static unsigned parts = 0;
+    if (!parts) {
+        const char* e = getenv("VKZG_TREE_THREADS");
+        unsigned hw = std::thread::hardware_concurrency();
+        parts = e ? (unsigned)atoi(e) : (hw > 8 ? 8u : (hw ? hw : 1u));
+        if (!parts) parts = 1;
+    }
+    return parts;
+}
+
 struct LevelBuf {
     std::vector<uint32_t> row_ptr{0};
     std::vector<uint16_t> slot;
@@ -403,12 +428,39 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     // everything and the cost stays proportional to the dirty paths.
     const bool bulk = raw && (ctx->tree_flatten == 1 || (ctx->tree_flatten == 0 && t->n_dirty * 8 > t->nodes.size()));
     if (bulk) {
+        // two passes on host threads over contiguous id ranges: count the dirty extensions of a range, then every range
+        // writes its records at its prefix offset — the same id order (hence the same rows) as one sequential pass
         const size_t nn = t->nodes.size();
-        for (size_t id = 0; id < nn; ++id) {
-            if (t->clean[id]) continue;  // a clean node's record is not even read
-            const HNode& n = t->nodes[id];
-            if (!n.internal) push_ext_compact((uint32_t)id, n);
-        }
+        const unsigned parts = host_parts();
+        std::vector<size_t> cnt(parts + 1, 0);
+        parallel_ranges(nn, parts, [&](size_t b, size_t e, unsigned p) {
+            size_t c = 0;
+            for (size_t id = b; id < e; ++id)
+                if (!t->clean[id] && !t->nodes[id].internal) ++c;  // a clean node's record is not even read
+            cnt[p + 1] = c;
+        });
+        for (unsigned p = 0; p < parts; ++p) cnt[p + 1] += cnt[p];
+        n_ext = cnt[parts];
+        if (n_ext > ext_cap) return VKZG_ERR_RANGE;  // cannot happen while n_dirty is maintained; never write past the staging area
+        levels[0].owner.assign(n_ext, 0xffffffffu);
+        levels[1].owner.resize(n_ext);
+        const uint32_t kl = t->key_len;
+        parallel_ranges(nn, parts, [&](size_t b, size_t e, unsigned p) {
+            size_t j = cnt[p];
+            for (size_t id = b; id < e; ++id) {
+                if (t->clean[id]) continue;
+                const HNode& n = t->nodes[id];
+                if (n.internal) continue;
+                fp_t st = fp_zero<S>();
+                memcpy(st.l, t->stem(n), kl);
+                ext_stem[j] = st;
+                memcpy(ext_val + j * 32, n.leaf_val.data(), 32);
+                ext_unit[j] = n.leaf_unit;
+                levels[1].owner[j] = (uint32_t)id;
+                handle[id] = {1u, (int32_t)j};
+                ++j;
+            }
+        });
     }
     while (!stack.empty()) {
         auto [id, done] = stack.back();
@@ -550,14 +602,17 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     VK_TRY(stream_sync(ctx));
     uint64_t off = 0;
     for (size_t l = 1; l < levels.size(); ++l) {
-        for (size_t j = 0; j < levels[l].owner.size(); ++j) {
-            uint32_t id = levels[l].owner[j];
-            if (id != 0xffffffffu) {
-                t->commits[id] = host[off + j];
-                t->clean[id] = 1;
+        const std::vector<uint32_t>& own = levels[l].owner;  // node ids are distinct: the ranges write disjoint entries
+        parallel_ranges(own.size(), host_parts(), [&](size_t b, size_t e, unsigned) {
+            for (size_t j = b; j < e; ++j) {
+                uint32_t id = own[j];
+                if (id != 0xffffffffu) {
+                    t->commits[id] = host[off + j];
+                    t->clean[id] = 1;
+                }
             }
-        }
-        off += levels[l].owner.size();
+        });
+        off += own.size();
     }
     if (timing) {
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
