@@ -14,7 +14,7 @@ $CMD2 > gpurun_out/plain_ipa_small.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_fixed_base_msm -s 5 -c 3 -f -o gpurun_out/r02_prof_ipa $CMD2 > gpurun_out/ncu_ipa_full.log 2>&1
 CMD3="python bench.py --workload msm --steps 2 --warmup 3 --no-cpu-baseline --no-also --no-check"
 $CMD3 > gpurun_out/plain_msm.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_msm_bucket -s 3 -c 1 -f -o gpurun_out/r02_prof_msm $CMD3 > gpurun_out/ncu_msm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_msm_bucket -s 4 -c 1 -f -o gpurun_out/r02_prof_msm $CMD3 > gpurun_out/ncu_msm.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_launches_bench_msm.csv $CMD3 > gpurun_out/ncu_msm_l.log 2>&1
 tail -3 gpurun_out/r02_gpu_tests.log; tail -c 600 gpurun_out/r02_bench_default.err
 ls -la gpurun_out/ | tail -20
