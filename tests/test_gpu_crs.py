@@ -87,3 +87,36 @@ def test_errors(eng):
     from verkle_kzg_b200._lib import VkzgError
     with pytest.raises(VkzgError):
         eng.ipa_crs_generate(b"x", 0)
+
+
+def test_setup_from_generators_like_the_reference(eng):
+    """IPA::setup(max_items, &IPAPointGenerator) (ipa/mod.rs:121-128) and KZG::setup(max_items, &KZGRandomPointGenerator)
+    (kzg/mod.rs:115-124) through the mirror: keys made on the GPU prove and verify like keys made from oracle points"""
+    from verkle_kzg_b200.vector_commit import IPA, KZG, IPAPointGenerator, KZGRandomPointGenerator, LagrangeBasis, OutOfBounds
+    N = 32
+    gen = IPAPointGenerator(eng, max=N + 1)
+    key = IPA.setup_from_generator(eng, N, gen, window_bits=8)
+    bases = orc.ipa_crs_gen(DEFAULT_SEED, N + 1)[0]
+    rng = np.random.default_rng(11)
+    data = LagrangeBasis(orc.rand_fr_buf(rng, N))
+    C = IPA.commit(key, data)
+    assert (C == orc.commit_batch(bases[:N], data.evaluations[None])[0]).all()
+    proof = IPA.prove(key, C, 3, data)
+    eL, eR, etip, ey = orc.ipa_prove(bases, N, data.evaluations, C, orc.fr_to_buf([3])[0])
+    assert (proof["l"] == eL).all() and (proof["r"] == eR).all() and (proof["tip"] == etip).all() and (proof["y"] == ey).all()
+    assert IPA.verify(key, C, 3, proof)
+    with pytest.raises(OutOfBounds):
+        IPA.setup_from_generator(eng, N + 1, gen)
+    key.free()
+    kgen = KZGRandomPointGenerator(eng)            # secret 100, kzg_point_generator.rs:20-26
+    assert kgen.secret() == 100
+    assert (kgen.gen(5) == orc.g1_mul_gen_batch(orc.fr_to_buf([pow(100, i, orc.R_MOD) for i in range(5)]))).all()
+    kkey = KZG.setup_from_generator(eng, 16, kgen, window_bits=8)
+    srs = orc.kzg_setup(16, 100)
+    d8 = LagrangeBasis.from_vec_and_domain(orc.rand_fr_buf(rng, 8), 16)
+    Ck = KZG.commit(kkey, d8)
+    assert (Ck == orc.commit_batch(srs[:8], d8.evaluations[None])[0]).all()
+    pf = KZG.prove(kkey, Ck, 5, d8)
+    epf, ey, ok = orc.kzg_prove(srs, d8.evaluations, orc.fr_to_buf([5])[0])
+    assert ok and (pf["proof"] == epf).all() and (pf["y"] == ey).all()
+    kkey.free()

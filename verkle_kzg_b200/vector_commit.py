@@ -17,6 +17,7 @@ import numpy as np
 from ._lib import KEY_WINDOW, VkzgError
 
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
 _MONT_R = 1 << 256
 
 
@@ -144,8 +145,39 @@ class _Scheme:
         return cls.verify_point(key, commitment, fr_from_int(index), proof)
 
 
+class KZGRandomPointGenerator:
+    """KZGRandomPointGenerator (kzg/kzg_point_generator.rs:10-52): the secret tau (default 100) and G * tau^i on the GPU"""
+
+    def __init__(self, engine, secret=100):
+        self.engine = engine
+        self._secret = int(secret) % R_MOD
+
+    def secret(self):
+        return self._secret
+
+    def _gen_key(self):
+        g = np.zeros((1, 64), dtype=np.uint8)
+        g[0, :32] = np.frombuffer((_MONT_R % _P_MOD).to_bytes(32, "little"), dtype=np.uint8)          # x = 1
+        g[0, 32:] = np.frombuffer((2 * _MONT_R % _P_MOD).to_bytes(32, "little"), dtype=np.uint8)      # y = 2
+        return self.engine.load_key(g, kind=KEY_WINDOW, window_bits=16)
+
+    def gen(self, num):
+        k = self._gen_key()
+        try:
+            return self.engine.kzg_powers(k, fr_from_int(self._secret), num)
+        finally:
+            k.free()
+
+
 class IPA(_Scheme):
     """IPA<N, G, H, D> (ipa/mod.rs:98-181)"""
+
+    @staticmethod
+    def setup_from_generator(engine, max_items, gen, window_bits=0):
+        """VectorCommitment::setup(max_items, gen) (ipa/mod.rs:121-128): gens = gen.gen(max_items + 1), g = the first
+        max_items of them, q the next one.  `gen` is an IPAPointGenerator (its bound raises OutOfBounds like the reference)."""
+        gens = gen.gen(max_items + 1)
+        return UniversalParams(engine, gens[:max_items], gens[max_items], window_bits)
 
     @staticmethod
     def prove_point(key, commitment, point, data, transcript=None):
@@ -199,6 +231,19 @@ class IPA(_Scheme):
 
 class KZG(_Scheme):
     """KZG<E, H, D> (kzg/mod.rs:96-198)"""
+
+    @staticmethod
+    def setup_from_generator(engine, max_items, gen, window_bits=0):
+        """VectorCommitment::setup(max_items, gen) (kzg/mod.rs:115-124): the Lagrange-form SRS over the radix-2 domain of size
+        next_pow2(max_items).  The reference runs `domain.ifft` over gen.gen(max_items); with the generator's secret at hand
+        (it is read there too, for the G2 element) the same canonical points come from closed-form scalars
+        (vkzg_kzg_setup_from_secret).  The G2 element of KZGKey stays on the host side of the shim (pairings, K4)."""
+        k = gen._gen_key()
+        try:
+            lagrange = engine.kzg_setup_from_secret(k, fr_from_int(gen.secret()), max_items)
+        finally:
+            k.free()
+        return UniversalParams(engine, lagrange, None, window_bits)
 
     @staticmethod
     def prove_point(key, commitment, point, data, transcript=None):
