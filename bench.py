@@ -887,6 +887,59 @@ def measure(ctx, wl, c, steps, warmup, sampler=None, cpu=True):
     return line
 
 
+def single_call_latencies(ctx, c):
+    """configs[0] as the reference's own criterion bench runs it (benches/kzg.rs:61-75, benches/ipa.rs:64-109): ONE vector per
+    call from host buffers, wall clock of the C-ABI call — the latency a drop-in caller of `commit` + `prove` sees — next to
+    the oracle's single-thread time for the same vector (the reference is single-threaded there).  Reported, not a metric."""
+    torch, eng, L = ctx.torch, ctx.eng, ctx.L
+    check = ctx._lib.check
+    orc = _orc()
+    key = ctx.key257(c)
+    kid = ctypes.c_uint32(key.id)
+    rng = np.random.default_rng(0xB1)
+    a_h, z_h = pinned(torch, (1, N_WIDTH, 32)), pinned(torch, (1, 32))
+    a_h.copy_(torch.from_numpy(orc.rand_fr_buf(rng, N_WIDTH).reshape(1, N_WIDTH, 32)))
+    z_h.copy_(torch.from_numpy(orc.fr_to_buf([77])))
+    C_h, P_h, R_h = pinned(torch, (1, 64)), pinned(torch, (1, 8, 64)), pinned(torch, (1, 8, 64))
+    tip_h, y_h = pinned(torch, (1, 32)), pinned(torch, (1, 32))
+    one = ctypes.c_uint64(1)
+
+    def kzg():
+        check(L.vkzg_kzg_commit_open_batch(eng._ctx, kid, hp(a_h), ctypes.c_uint32(N_WIDTH), ctypes.c_uint32(0), hp(z_h), one, hp(C_h), hp(P_h),
+                                           hp(y_h)), "commit+open")
+
+    def ipa():
+        check(L.vkzg_ipa_commit_prove_batch(eng._ctx, kid, hp(a_h), hp(z_h), one, hp(C_h), hp(P_h), hp(R_h), hp(tip_h), hp(y_h)), "commit+prove")
+
+    out = {}
+    an, zn = a_h.numpy(), z_h.numpy()
+    for name, fn in (("kzg_commit_open", kzg), ("ipa_commit_prove", ipa)):
+        for _ in range(5):
+            fn()
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        eC = orc.commit_batch(ctx.bases_h[:N_WIDTH], an)[0]
+        t0 = time.perf_counter()
+        if name == "kzg_commit_open":
+            orc.commit_batch(ctx.bases_h[:N_WIDTH], an, nthreads=1)
+            epf, ey, ok = orc.kzg_prove(ctx.bases_h[:N_WIDTH], an[0], zn[0])
+            good = ok and (P_h.numpy().reshape(-1)[:64] == epf).all() and (y_h.numpy()[0] == ey).all() and (C_h.numpy()[0] == eC).all()
+        else:
+            orc.commit_batch(ctx.bases_h[:N_WIDTH], an, nthreads=1)
+            eL, eR, etip, ey = orc.ipa_prove(ctx.bases_h, N_WIDTH, an[0], eC, zn[0])
+            good = ((P_h.numpy()[0] == eL).all() and (R_h.numpy()[0] == eR).all() and (tip_h.numpy()[0] == etip).all()
+                    and (y_h.numpy()[0] == ey).all() and (C_h.numpy()[0] == eC).all())
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        out[name] = {"ms_median": round(float(np.median(ts)) * 1e3, 4), "ms_min": round(min(ts) * 1e3, 4), "cpu_ms_1thread": round(cpu_ms, 2),
+                     "matches_oracle": bool(good)}
+    out["note"] = ("one width-256 vector per call, host buffers, wall clock around the C-ABI call (B = 1: latency-bound, DESIGN.md "
+                   "section 4); cpu = the oracle's restatement on ONE host thread, as the reference runs it")
+    return out
+
+
 def condensed(line):
     """what an `also` entry keeps of a full line"""
     r = line["roofline"]
@@ -925,6 +978,12 @@ def run_native(args):
                 also[name] = {"error": str(e)}
                 failed = True
         line["also"] = also
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["single_call"] = single_call_latencies(ctx, c)
+                failed = failed or not all(v["matches_oracle"] for v in line["single_call"].values() if isinstance(v, dict))
+            except Exception as e:   # a reported extra must not take the bench line down
+                line["single_call"] = {"error": repr(e)}
     if rank == 0:
         emit(line)
     if world > 1:
