@@ -66,7 +66,8 @@ VK_HD xyzz_t xyzz_dbl(const xyzz_t& p) {
     fp_t M = fp_add<Q>(fp_dbl<Q>(X2), X2);
     xyzz_t r;
     r.x = fp_sub<Q>(fp_sqr<Q>(M), fp_dbl<Q>(Sx));
-    r.y = fp_sub<Q>(fp_mul<Q>(M, fp_sub<Q>(Sx, r.x)), fp_mul<Q>(W, p.y));
+    // Y3 = M (S - X3) - W Y1 as one fused pair of products (one Montgomery reduction, field.cuh: fp_mul2_lazy)
+    r.y = fp_canon<Q>(fp_mul2_lazy<Q>(M, fp_sub<Q>(Sx, r.x), W, fp_neg<Q>(p.y)));
     r.zz = fp_mul<Q>(V, p.zz);
     r.zzz = fp_mul<Q>(W, p.zzz);
     return r;
@@ -175,7 +176,7 @@ VK_HD xyzz_t xyzz_add(const xyzz_t& a, const xyzz_t& b) {
     fp_t Qv = fp_mul<Q>(U1, PP);
     xyzz_t r;
     r.x = fp_sub<Q>(fp_sub<Q>(fp_sqr<Q>(R), PPP), fp_dbl<Q>(Qv));
-    r.y = fp_sub<Q>(fp_mul<Q>(R, fp_sub<Q>(Qv, r.x)), fp_mul<Q>(S1, PPP));
+    r.y = fp_canon<Q>(fp_mul2_lazy<Q>(R, fp_sub<Q>(Qv, r.x), fp_neg<Q>(S1), PPP));  // R (Q - X3) - S1 PPP, fused pair
     r.zz = fp_mul<Q>(fp_mul<Q>(a.zz, b.zz), PP);
     r.zzz = fp_mul<Q>(fp_mul<Q>(a.zzz, b.zzz), PPP);
     return r;
