@@ -268,3 +268,29 @@ def test_sharded_msm_and_batches_over_gloo_world2(tmp_path):
                           "--master-port", "29531", str(script), ROOT], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def _build_c_caller(tmp_path):
+    """examples/abi_smoke.c: a plain C99 translation unit against include/vkzg.h, linked with libvkzg.so"""
+    exe = os.path.join(str(tmp_path), "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_smoke.c"), "-L", os.path.join(ROOT, "verkle_kzg_b200"), "-lvkzg",
+                           "-Wl,-rpath," + os.path.join(ROOT, "verkle_kzg_b200"), "-o", exe])
+    return exe
+
+
+def test_header_is_valid_c_and_the_library_links_from_c(vk, tmp_path):
+    """the drop-in boundary is a C ABI: the header compiles as pedantic C99, the library links from C, and without a GPU
+    the C caller sees VKZG_ERR_CUDA (no CPU fallback) — with one it commits (test below)"""
+    exe = _build_c_caller(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi 1" in r.stdout
+    assert ("no device" in r.stdout) or ("commit ok" in r.stdout)
+
+
+@pytest.mark.gpu
+def test_c_caller_commits_on_the_gpu(tmp_path):
+    exe = _build_c_caller(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "commit ok" in r.stdout, r.stdout + r.stderr
