@@ -462,6 +462,7 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
             }
         });
     }
+    auto t_bulk = now();
     while (!stack.empty()) {
         auto [id, done] = stack.back();
         stack.pop_back();
@@ -616,8 +617,8 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     }
     if (timing) {
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "vkzg_tree_commit: %zu rows; flatten %.1f ms, sort+ids %.1f ms, upload+kernels %.1f ms, cache-back %.1f ms\n",
-                n_new, ms(t_start, t_flat), ms(t_flat, t_ids), ms(t_ids, t_dev), ms(t_dev, now()));
+        fprintf(stderr, "vkzg_tree_commit: %zu rows; flatten %.1f ms (setup + bulk pass %.1f, walk %.1f), sort+ids %.1f ms, upload+kernels %.1f ms, cache-back %.1f ms\n",
+                n_new, ms(t_start, t_flat), ms(t_start, t_bulk), ms(t_bulk, t_flat), ms(t_flat, t_ids), ms(t_ids, t_dev), ms(t_dev, now()));
     }
     t->n_dirty = 0;
     if (n_committed) *n_committed = n_new;
