@@ -219,8 +219,8 @@ static fp_t fr_from_le_bytes(const uint8_t* b, size_t len) {
 
 // f(begin, end, part) over `parts` contiguous ranges of [0, n) on host threads (part 0 on the caller's)
 template <class F>
-static void parallel_ranges(size_t n, unsigned parts, F&& f) {
-    if (parts <= 1 || n < 4096) {
+static void parallel_ranges(size_t n, unsigned parts, F&& f, size_t min_n = 4096) {
+    if (parts <= 1 || n < min_n) {
         f((size_t)0, n, 0u);
         return;
     }
@@ -404,7 +404,6 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     ++t->n_commits;
     std::vector<affine_t> known;            // commitments of clean children referenced by dirty parents
     std::vector<std::pair<uint32_t, int32_t>> handle(t->nodes.size(), {0xffffffffu, -1});  // node -> (level, row) ; level 0xfffffffe = known
-    std::vector<std::pair<uint32_t, bool>> stack{{0u, false}};
     const fp_t one = fp_one<S>(), zero = fp_zero<S>();
     bool overflow = false;
     auto push_ext_compact = [&](uint32_t id, const HNode& n) {
@@ -463,12 +462,17 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         });
     }
     auto t_bulk = now();
+    // depth-first walk from `start`: rows go to `levels`, commitments of clean children to `known` (+ their node ids to
+    // `known_ids` when the caller has to re-base them after a merge)
+    auto walk = [&](uint32_t start, std::vector<LevelBuf>& levels, std::vector<affine_t>& known, std::vector<uint32_t>* known_ids) {
+    std::vector<std::pair<uint32_t, bool>> stack{{start, false}};
     while (!stack.empty()) {
         auto [id, done] = stack.back();
         stack.pop_back();
         if (t->clean[id]) {
             known.push_back(t->commits[id]);
             handle[id] = {0xfffffffeu, (int32_t)known.size() - 1};
+            if (known_ids) known_ids->push_back(id);
             continue;
         }
         HNode& n = t->nodes[id];
@@ -508,6 +512,9 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
             cu[nc] = u;
             cc[nc++] = c;
         });
+        // the children's handles are scattered over the node-id space (ids follow insertion order): request them all before
+        // the first one is read, so that the misses overlap instead of queueing (63 -> see DESIGN.md ms at 2^20 keys)
+        for (uint32_t j = 0; j < nc; ++j) __builtin_prefetch(&handle[cc[j]]);
         if (!done) {
             for (uint32_t j = 0; j < nc; ++j)
                 if (handle[cc[j]].first == 0xffffffffu) {  // not placed yet (bulk: the dirty extensions already have their row)
@@ -525,6 +532,47 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         for (uint32_t j = 0; j < nc; ++j) levels[level].term_child(cu[j], (int32_t)cc[j]);
         handle[id] = {level, (int32_t)levels[level].close(id)};
     }
+    };
+    // Bulk mode with a wide root (the first commit of a loaded tree): the subtrees under the root's children are walked on
+    // host threads into thread-local rows and merged (rows re-based, handles shifted); the extensions already have their
+    // rows from the bulk pass, so the walks share nothing but the handle array, which they write at disjoint node ids.
+    // A walk is ~1 us of dependent cache misses per internal node (65 k of them at 2^20 keys: 63 ms on one thread).
+    {
+        std::vector<uint32_t> subs;
+        if (bulk && host_parts() > 1 && !t->clean[0] && t->nodes[0].internal)
+            t->for_each_child(t->nodes[0], [&](uint8_t, uint32_t c) {
+                if (!t->clean[c] && t->nodes[c].internal) subs.push_back(c);
+            });
+        const unsigned parts = (unsigned)std::min<size_t>(host_parts(), subs.size() / 4);
+        if (parts > 1) {
+            std::vector<std::vector<LevelBuf>> lv(parts);
+            std::vector<std::vector<affine_t>> kn(parts);
+            std::vector<std::vector<uint32_t>> kid(parts);
+            parallel_ranges(subs.size(), parts, [&](size_t b, size_t e, unsigned p) {
+                for (size_t i = b; i < e; ++i) walk(subs[i], lv[p], kn[p], &kid[p]);
+            }, /*min_n=*/0);
+            for (unsigned p = 0; p < parts; ++p) {
+                const int32_t koff = (int32_t)known.size();
+                known.insert(known.end(), kn[p].begin(), kn[p].end());
+                if (koff)
+                    for (uint32_t id : kid[p]) handle[id].second += koff;
+                if (levels.size() < lv[p].size()) levels.resize(lv[p].size());
+                for (size_t l = 2; l < lv[p].size(); ++l) {
+                    LevelBuf& D = levels[l];
+                    const LevelBuf& Sx = lv[p][l];
+                    const int32_t roff = (int32_t)D.owner.size();
+                    const uint32_t toff = (uint32_t)D.slot.size();
+                    D.slot.insert(D.slot.end(), Sx.slot.begin(), Sx.slot.end());
+                    D.child.insert(D.child.end(), Sx.child.begin(), Sx.child.end());
+                    for (size_t r = 1; r < Sx.row_ptr.size(); ++r) D.row_ptr.push_back(Sx.row_ptr[r] + toff);
+                    D.owner.insert(D.owner.end(), Sx.owner.begin(), Sx.owner.end());
+                    if (roff)
+                        for (uint32_t id : Sx.owner) handle[id].second += roff;
+                }
+            }
+        }
+    }
+    walk(0u, levels, known, nullptr);
     if (overflow) return VKZG_ERR_RANGE;
     auto t_flat = now();
     // ---- internal levels: order the nodes of a level by their number of children, so that the lanes / groups of one
@@ -559,11 +607,15 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
     if (total >= (1ull << 31)) return VKZG_ERR_RANGE;
     for (auto& c : levels[1].child)
         if (c <= -2) c = (int32_t)(base[0] + (uint64_t)(-c - 2));
-    for (size_t l = 2; l < levels.size(); ++l)
-        for (auto& c : levels[l].child) {
-            auto h = handle[(uint32_t)c];
-            c = h.first == 0xfffffffeu ? h.second : (int32_t)(base[h.first] + (uint64_t)h.second);
+    for (size_t l = 2; l < levels.size(); ++l) {
+        std::vector<int32_t>& ch = levels[l].child;
+        const size_t nch = ch.size();
+        for (size_t i = 0; i < nch; ++i) {
+            if (i + 16 < nch) __builtin_prefetch(&handle[(uint32_t)ch[i + 16]]);
+            auto h = handle[(uint32_t)ch[i]];
+            ch[i] = h.first == 0xfffffffeu ? h.second : (int32_t)(base[h.first] + (uint64_t)h.second);
         }
+    }
     auto t_ids = now();
     // ---- device passes
     DevBuf<affine_t> all;
