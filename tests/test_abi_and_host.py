@@ -294,3 +294,25 @@ def test_c_caller_commits_on_the_gpu(tmp_path):
     exe = _build_c_caller(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "commit ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("mode,n,kl", [("uniform", 20000, 32), ("narrow", 8000, 8), ("dups", 6000, 32), ("panic", 5000, 6)])
+def test_bulk_load_on_host_threads_equals_the_sequential_insertion(vk, mode, n, kl):
+    """vkzg_tree_insert into an empty tree groups the pairs by first unit and builds the subtrees on host threads; the
+    structure must be the one Node::insert (node.rs:133-197) builds pair by pair: same node count, same lookups (present,
+    absent, overwritten), same paths, and — where the reference panics — the same error and the same count of pairs
+    inserted (the threaded load falls back to the sequential loop).  Host-only: no GPU involved."""
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tree_host_probe.py")
+    outs = []
+    for threads in ("1", "4"):
+        env = dict(os.environ, VKZG_ROOT=ROOT, VKZG_TREE_THREADS=threads, VKZG_TREE_PAR_MIN="1000")
+        r = subprocess.run([sys.executable, probe, "11", str(n), str(kl), mode], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
+    import json
+    d = json.loads(outs[0])
+    if mode == "panic":
+        assert d["status"] == -3 and 0 < d["done"] < n
+    else:
+        assert d["status"] == 0 and d["done"] == n

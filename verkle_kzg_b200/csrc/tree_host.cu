@@ -284,34 +284,143 @@ int32_t vkzg_tree_destroy(vkzg_tree* t) {
     return VKZG_OK;
 }
 
-// n (key, value) pairs inserted IN ORDER; stops at the first pair the reference would panic on (VKZG_ERR_RANGE,
-// *n_done = pairs inserted)
-int32_t vkzg_tree_insert(vkzg_tree* t, const uint8_t* keys, const uint8_t* values, uint64_t n, uint64_t* n_done) {
-    if (!t || (n && (!keys || !values))) return VKZG_ERR_ARG;
-    t->nodes.reserve(t->nodes.size() + n + n / 4 + 16);
-    t->stems.reserve(t->stems.size() + n * t->key_len);
-    t->tables.reserve(t->tables.size() + 256 * (n / 13 + 16));
+// the sequential insertion loop (with the staged software prefetch); returns the number of pairs inserted
+static uint64_t insert_run(vkzg_tree* t, const uint8_t* keys, const uint8_t* values, const uint32_t* order, uint64_t n) {
     const uint64_t kl = t->key_len;
-    const bool timing = getenv("VKZG_TREE_TIMING") != nullptr;
-    auto t_start = std::chrono::steady_clock::now();
+    auto at = [&](uint64_t i) { return order ? (uint64_t)order[i] : i; };
     for (uint64_t i = 0; i < n; ++i) {
         // staged look-ahead: deeper levels of nearer keys (each stage reads only what an earlier stage prefetched)
         // (root and the level-1 nodes stay cached: reads 0..3 are hits; 4 = level-2 header, 5 = its slot, 6 = the
         // level-3 node (usually the extension), whose stem is the last line an insertion compares)
-        if (i + 16 < n) t->prefetch_path(keys + (i + 16) * kl, 4);
-        if (i + 12 < n) t->prefetch_path(keys + (i + 12) * kl, 5);
-        if (i + 8 < n) t->prefetch_path(keys + (i + 8) * kl, 6);
-        if (i + 4 < n) t->prefetch_path(keys + (i + 4) * kl, 7);
-        if (!t->insert(keys + i * t->key_len, values + i * 32)) {
-            if (n_done) *n_done = i;
-            return VKZG_ERR_RANGE;
+        if (i + 16 < n) t->prefetch_path(keys + at(i + 16) * kl, 4);
+        if (i + 12 < n) t->prefetch_path(keys + at(i + 12) * kl, 5);
+        if (i + 8 < n) t->prefetch_path(keys + at(i + 8) * kl, 6);
+        if (i + 4 < n) t->prefetch_path(keys + at(i + 4) * kl, 7);
+        if (!t->insert(keys + at(i) * kl, values + at(i) * 32)) return i;
+    }
+    return n;
+}
+
+// Bulk load into an EMPTY tree on host threads.  The subtrees under different first units never interact (Node::insert walks
+// down from the root by key[0]), so the pairs are grouped by key[0] (stable: the order inside a group is the caller's), every
+// thread builds the subtrees of a contiguous range of first units in a tree of its own with the very same insert code, and
+// the partial trees are spliced under the real root (node ids, stem offsets and table ids re-based).  Any pair the
+// reference would panic on makes the whole load fall back to the sequential loop, which reports the exact count.
+static bool insert_parallel(vkzg_tree* t, const uint8_t* keys, const uint8_t* values, uint64_t n, unsigned parts) {
+    const uint64_t kl = t->key_len;
+    std::vector<uint64_t> cnt(257, 0);
+    for (uint64_t i = 0; i < n; ++i) ++cnt[keys[i * kl] + 1];
+    for (int u = 0; u < 256; ++u) cnt[u + 1] += cnt[u];
+    std::vector<uint32_t> order(n);
+    {
+        std::vector<uint64_t> cur(cnt.begin(), cnt.end() - 1);
+        for (uint64_t i = 0; i < n; ++i) order[cur[keys[i * kl]]++] = (uint32_t)i;
+    }
+    // contiguous ranges of first units with about n / parts pairs each
+    std::vector<uint32_t> cut(parts + 1, 256);
+    cut[0] = 0;
+    for (unsigned p = 1; p < parts; ++p) {
+        uint32_t u = cut[p - 1];
+        while (u < 256 && cnt[u] < n * p / parts) ++u;
+        cut[p] = u;
+    }
+    std::vector<vkzg_tree> part(parts);
+    std::vector<uint8_t> ok(parts, 1);
+    auto build = [&](unsigned p) {
+        vkzg_tree& lt = part[p];
+        lt.key_len = t->key_len;
+        lt.ext_width = t->ext_width;
+        lt.nodes.emplace_back();
+        const uint64_t b = cnt[cut[p]], e = cnt[cut[p + 1]], m = e - b;
+        lt.nodes.reserve(m + m / 4 + 16);
+        lt.stems.reserve(m * kl);
+        lt.tables.reserve(256 * (m / 13 + 16));
+        ok[p] = insert_run(&lt, keys, values, order.data() + b, m) == m;
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned p = 1; p < parts; ++p) th.emplace_back(build, p);
+        build(0);
+        for (auto& x : th) x.join();
+    }
+    for (unsigned p = 0; p < parts; ++p)
+        if (!ok[p]) return false;
+    // ---- splice: node 0 of every partial tree is its private root; its other nodes move to id base[p] + (local id - 1)
+    std::vector<uint64_t> nbase(parts + 1), sbase(parts + 1), tbase(parts + 1);
+    nbase[0] = t->nodes.size();
+    sbase[0] = t->stems.size();
+    tbase[0] = t->tables.size() / 256;
+    for (unsigned p = 0; p < parts; ++p) {
+        nbase[p + 1] = nbase[p] + part[p].nodes.size() - 1;
+        sbase[p + 1] = sbase[p] + part[p].stems.size();
+        tbase[p + 1] = tbase[p] + part[p].tables.size() / 256;
+    }
+    if (nbase[parts] >= (1ull << 31)) return false;
+    t->nodes.resize(nbase[parts]);
+    t->stems.resize(sbase[parts]);
+    t->tables.resize(tbase[parts] * 256);
+    auto splice = [&](unsigned p) {
+        const vkzg_tree& lt = part[p];
+        const int64_t shift = (int64_t)nbase[p] - 1;
+        for (size_t i = 1; i < lt.nodes.size(); ++i) {
+            HNode nd = lt.nodes[i];
+            if (nd.internal) {
+                for (uint32_t j = 0; j < nd.nk; ++j) nd.kid[j] = (uint32_t)(nd.kid[j] + shift);
+                if (nd.table_id >= 0) nd.table_id += (int32_t)tbase[p];
+            } else {
+                nd.stem_off += sbase[p];
+            }
+            t->nodes[nbase[p] + i - 1] = nd;
         }
+        if (!lt.stems.empty()) memcpy(t->stems.data() + sbase[p], lt.stems.data(), lt.stems.size());
+        int32_t* dst = t->tables.data() + tbase[p] * 256;
+        for (size_t i = 0; i < lt.tables.size(); ++i) dst[i] = lt.tables[i] < 0 ? -1 : (int32_t)(lt.tables[i] + shift);
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned p = 1; p < parts; ++p) th.emplace_back(splice, p);
+        splice(0);
+        for (auto& x : th) x.join();
+    }
+    for (unsigned p = 0; p < parts; ++p) {
+        const vkzg_tree& lt = part[p];
+        const int64_t shift = (int64_t)nbase[p] - 1;
+        // (a private root that outgrew its inline list owns table 0 of its tree; that table is spliced but unused)
+        lt.for_each_child(lt.nodes[0], [&](uint8_t u, uint32_t c) { t->set_child(0, u, (uint32_t)(c + shift)); });
+        t->n_keys += lt.n_keys;
+        t->n_dirty += lt.n_dirty - 1;  // (every tree counted its own root)
+    }
+    return true;
+}
+
+// n (key, value) pairs inserted IN ORDER; stops at the first pair the reference would panic on (VKZG_ERR_RANGE,
+// *n_done = pairs inserted)
+int32_t vkzg_tree_insert(vkzg_tree* t, const uint8_t* keys, const uint8_t* values, uint64_t n, uint64_t* n_done) {
+    if (!t || (n && (!keys || !values))) return VKZG_ERR_ARG;
+    const bool timing = getenv("VKZG_TREE_TIMING") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    static uint64_t par_min = 0;
+    if (!par_min) {
+        const char* e = getenv("VKZG_TREE_PAR_MIN");
+        par_min = e ? strtoull(e, nullptr, 10) : 65536;
+        if (!par_min) par_min = 1;
+    }
+    bool done = false;
+    if (t->nodes.size() == 1 && t->nodes[0].nk == 0 && t->nodes[0].table_id < 0 && n >= par_min && n < (1ull << 32) && host_parts() > 1)
+        done = insert_parallel(t, keys, values, n, host_parts());
+    uint64_t inserted = n;
+    if (!done) {
+        t->nodes.reserve(t->nodes.size() + n + n / 4 + 16);
+        t->stems.reserve(t->stems.size() + n * t->key_len);
+        t->tables.reserve(t->tables.size() + 256 * (n / 13 + 16));
+        inserted = insert_run(t, keys, values, nullptr, n);
     }
     if (timing)
-        fprintf(stderr, "vkzg_tree_insert: %llu keys in %.1f ms\n", (unsigned long long)n,
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
-    if (n_done) *n_done = n;
-    return VKZG_OK;
+        fprintf(stderr, "vkzg_tree_insert: %llu keys in %.1f ms%s\n", (unsigned long long)inserted,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(),
+                done ? " (bulk load on host threads)" : "");
+    if (n_done) *n_done = inserted;
+    return inserted == n ? VKZG_OK : VKZG_ERR_RANGE;
 }
 
 // returns 1 and copies the 32-byte value if present, 0 otherwise
