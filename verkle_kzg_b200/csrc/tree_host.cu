@@ -308,6 +308,10 @@ static uint64_t insert_run(vkzg_tree* t, const uint8_t* keys, const uint8_t* val
 // reference would panic on makes the whole load fall back to the sequential loop, which reports the exact count.
 static bool insert_parallel(vkzg_tree* t, const uint8_t* keys, const uint8_t* values, uint64_t n, unsigned parts) {
     const uint64_t kl = t->key_len;
+    const bool timing = getenv("VKZG_TREE_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t0 = now();
     std::vector<uint64_t> cnt(257, 0);
     for (uint64_t i = 0; i < n; ++i) ++cnt[keys[i * kl] + 1];
     for (int u = 0; u < 256; ++u) cnt[u + 1] += cnt[u];
@@ -324,6 +328,7 @@ static bool insert_parallel(vkzg_tree* t, const uint8_t* keys, const uint8_t* va
         while (u < 256 && cnt[u] < n * p / parts) ++u;
         cut[p] = u;
     }
+    auto t1 = now();
     std::vector<vkzg_tree> part(parts);
     std::vector<uint8_t> ok(parts, 1);
     auto build = [&](unsigned p) {
@@ -338,18 +343,21 @@ static bool insert_parallel(vkzg_tree* t, const uint8_t* keys, const uint8_t* va
         ok[p] = insert_run(&lt, keys, values, order.data() + b, m) == m;
     };
     {
+        // (touching the final arenas on one more thread meanwhile was measured: the page faults of nine threads serialise in
+        //  the kernel and the build phase goes from 25 to 82 ms — the arenas are sized after the builds instead, 19 ms)
         std::vector<std::thread> th;
         for (unsigned p = 1; p < parts; ++p) th.emplace_back(build, p);
         build(0);
         for (auto& x : th) x.join();
     }
     for (unsigned p = 0; p < parts; ++p)
-        if (!ok[p]) return false;
+        if (!ok[p]) return false;  // the tree is untouched: the sequential loop takes over
+    auto t2 = now();
     // ---- splice: node 0 of every partial tree is its private root; its other nodes move to id base[p] + (local id - 1)
     std::vector<uint64_t> nbase(parts + 1), sbase(parts + 1), tbase(parts + 1);
-    nbase[0] = t->nodes.size();
-    sbase[0] = t->stems.size();
-    tbase[0] = t->tables.size() / 256;
+    nbase[0] = 1;  // (the tree was empty: only its root)
+    sbase[0] = 0;
+    tbase[0] = 0;
     for (unsigned p = 0; p < parts; ++p) {
         nbase[p + 1] = nbase[p] + part[p].nodes.size() - 1;
         sbase[p + 1] = sbase[p] + part[p].stems.size();
@@ -358,7 +366,9 @@ static bool insert_parallel(vkzg_tree* t, const uint8_t* keys, const uint8_t* va
     if (nbase[parts] >= (1ull << 31)) return false;
     t->nodes.resize(nbase[parts]);
     t->stems.resize(sbase[parts]);
+    t->tables.reserve(tbase[parts] * 256 + 256);  // (+ the root's own table, allocated by the set_child calls below: no regrowth)
     t->tables.resize(tbase[parts] * 256);
+    auto t3 = now();
     auto splice = [&](unsigned p) {
         const vkzg_tree& lt = part[p];
         const int64_t shift = (int64_t)nbase[p] - 1;
@@ -390,6 +400,9 @@ static bool insert_parallel(vkzg_tree* t, const uint8_t* keys, const uint8_t* va
         t->n_keys += lt.n_keys;
         t->n_dirty += lt.n_dirty - 1;  // (every tree counted its own root)
     }
+    if (timing)
+        fprintf(stderr, "vkzg_tree_insert (threads): group %.1f ms, build %.1f ms, resize %.1f ms, splice %.1f ms\n", ms(t0, t1), ms(t1, t2),
+                ms(t2, t3), ms(t3, now()));
     return true;
 }
 
