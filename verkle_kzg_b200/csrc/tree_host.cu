@@ -731,12 +731,13 @@ int32_t vkzg_tree_commit(vkzg_ctx* ctx, uint32_t key_id, vkzg_tree* t, vkzg_g1_a
         if (c <= -2) c = (int32_t)(base[0] + (uint64_t)(-c - 2));
     for (size_t l = 2; l < levels.size(); ++l) {
         std::vector<int32_t>& ch = levels[l].child;
-        const size_t nch = ch.size();
-        for (size_t i = 0; i < nch; ++i) {
-            if (i + 16 < nch) __builtin_prefetch(&handle[(uint32_t)ch[i + 16]]);
-            auto h = handle[(uint32_t)ch[i]];
-            ch[i] = h.first == 0xfffffffeu ? h.second : (int32_t)(base[h.first] + (uint64_t)h.second);
-        }
+        parallel_ranges(ch.size(), host_parts(), [&](size_t b, size_t e, unsigned) {  // (scattered reads of the handle array)
+            for (size_t i = b; i < e; ++i) {
+                if (i + 16 < e) __builtin_prefetch(&handle[(uint32_t)ch[i + 16]]);
+                auto h = handle[(uint32_t)ch[i]];
+                ch[i] = h.first == 0xfffffffeu ? h.second : (int32_t)(base[h.first] + (uint64_t)h.second);
+            }
+        });
     }
     auto t_ids = now();
     // ---- device passes
