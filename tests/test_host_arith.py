@@ -86,6 +86,35 @@ def test_lazy_reduction_ops(hc, tag, mod):
 
 
 @pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
+def test_dedicated_square(hc, tag, mod):
+    """fp_sqr_lazy: a^2 / R with 36 instead of 64 limb products (doubled off-diagonal rows interleaved with the reduction),
+    operand anywhere in [0, 2p]; the raw result must respect the [0, 2p) invariant of the hot loops"""
+    rng = np.random.default_rng(700 + tag)
+    edge = [0, 1, 2, mod - 1, mod, mod + 1, 2 * mod - 1, 2 * mod, (1 << 254) - 1, (1 << 254), mod + (1 << 253), 2 * mod - (1 << 32),
+            (1 << 255) % (2 * mod), (1 << 31), (1 << 32) - 1, (1 << 63), ((1 << 224) - 1) << 29]
+    # limb patterns that stress the doubled rows: bit 31 of every limb set / only the top bits / alternating all-ones limbs
+    pat = [sum(0x80000000 << (32 * i) for i in range(8)), sum(0xFFFFFFFF << (32 * i) for i in range(0, 8, 2)),
+           sum(0xFFFFFFFF << (32 * i) for i in range(1, 8, 2)), sum(0x80000001 << (32 * i) for i in range(8)), (1 << 256) - 1]
+    edge += [v % (2 * mod + 1) for v in pat] + [min(v, 2 * mod) for v in pat]
+    for top in range(0, 0x61):  # every value of the top byte that keeps the operand <= 2p, all other bits set
+        v = (top << 248) | ((1 << 248) - 1)
+        if v <= 2 * mod:
+            edge.append(v)
+    xs = [int.from_bytes(rng.bytes(32), "little") % (2 * mod + 1) for _ in range(3000)] + edge
+    raw = lambda v: np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in v), dtype=np.uint8).reshape(-1, 32).copy()
+    a = raw(xs)
+    rinv = pow(orc.MONT_R, -1, mod)
+    val = lambda buf: [int.from_bytes(bytes(r), "little") for r in buf]
+    want = [(x * x * rinv) % mod for x in xs]
+    assert val(_op(hc, tag, 11, a)) == want
+    got = val(_op(hc, tag, 12, a))
+    assert all(g < 2 * mod for g in got)
+    assert [g % mod for g in got] == want
+    # and it is the same function as the general lazy product on equal operands
+    assert val(_op(hc, tag, 8, a, a)) == want
+
+
+@pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
 def test_fused_pair_of_products(hc, tag, mod):
     """fp_mul2_lazy: (a b + c d) / R in one interleaved Montgomery pass, operands anywhere in [0, 2p] (2p itself is what
     fp_neg_lazy returns for 0); the raw result must respect the [0, 2p) invariant of the hot loops"""

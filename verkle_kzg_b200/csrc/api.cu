@@ -362,6 +362,18 @@ __global__ void __launch_bounds__(256) k_probe_fq_mul(fp_t* x, const fp_t* y, ui
     fp_store(x + i, a);
 }
 
+// x <- x^(2^iters) through the hot loops' out-of-line multipliers: MODE 0 the dedicated square (fp_sqr_lazy), 1 the general
+// lazy product on equal operands.  The device-side check of the square's carry chains and its throughput probe.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_probe_fq_sqr(fp_t* x, uint64_t n, uint32_t iters) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp_t a = fp_load(x + i);
+#pragma unroll 1
+    for (uint32_t k = 0; k < iters; ++k) a = MODE == 0 ? fp_sqr_lazy_ni<Q>(a) : fp_mul_lazy_ni<Q>(a, a);
+    fp_store(x + i, fp_canon<Q>(a));
+}
+
 // 8 independent accumulator chains per thread, 8 instructions per chain per iteration
 template <int KIND>
 __global__ void __launch_bounds__(256) k_probe_imad(uint32_t iters, uint64_t* sink) {
@@ -441,6 +453,16 @@ int32_t vkzg_probe_fq_mul_dev(vkzg_ctx* ctx, vkzg_fq* d_x, const vkzg_fq* d_y, u
     VK_TRY(ctx_check(ctx));
     if (!d_x || !d_y || !n) return VKZG_ERR_ARG;
     k_probe_fq_mul<<<ceil_div_u64(n, 256), 256, 0, ctx->stream>>>((fp_t*)d_x, (const fp_t*)d_y, n, iters);
+    return launch_check(ctx);
+}
+
+int32_t vkzg_probe_fq_sqr_dev(vkzg_ctx* ctx, vkzg_fq* d_x, uint64_t n, uint32_t iters, uint32_t mode) {
+    VK_TRY(ctx_check(ctx));
+    if (!d_x || !n || mode > 1) return VKZG_ERR_ARG;
+    if (mode == 0)
+        k_probe_fq_sqr<0><<<ceil_div_u64(n, 256), 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters);
+    else
+        k_probe_fq_sqr<1><<<ceil_div_u64(n, 256), 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters);
     return launch_check(ctx);
 }
 

@@ -114,9 +114,11 @@ VK_HD void xyzz_madd(xyzz_t& acc, const affine_t& p) {
 #ifdef __CUDA_ARCH__
 #define VK_MUL_HOT(a, b) fp_mul_lazy_ni<Q>(a, b)  // (fully inlined was measured slower: 164 k vs 173 k proofs/s)
 #define VK_MUL2_HOT(a, b, c, d) fp_mul2_lazy_ni<Q>(a, b, c, d)
+#define VK_SQR_HOT(a) fp_sqr_lazy_ni<Q>(a)        // 108 instead of 136 multiply-accumulates (field.cuh: fp_sqr_lazy)
 #else
 #define VK_MUL_HOT(a, b) fp_mul_lazy<Q>(a, b)
 #define VK_MUL2_HOT(a, b, c, d) fp_mul2_lazy<Q>(a, b, c, d)
+#define VK_SQR_HOT(a) fp_sqr_lazy<Q>(a)
 #endif
 // The accumulator coordinates are kept in [0, 2p) ("almost Montgomery": no final conditional subtraction in the ten
 // products); xyzz_canon() brings them back to [0, p) once, after the loop.  The table point is canonical.
@@ -137,10 +139,10 @@ __host__ __device__ __forceinline__ void xyzz_madd_hot(xyzz_t& acc, const affine
             acc = xyzz_inf();
         return;
     }
-    fp_t PP = VK_MUL_HOT(P, P);
+    fp_t PP = VK_SQR_HOT(P);
     fp_t PPP = VK_MUL_HOT(P, PP);
     fp_t Qv = VK_MUL_HOT(acc.x, PP);
-    fp_t X3 = fp_sub_lazy<Q>(fp_sub_lazy<Q>(VK_MUL_HOT(R, R), PPP), fp_add_lazy<Q>(Qv, Qv));
+    fp_t X3 = fp_sub_lazy<Q>(fp_sub_lazy<Q>(VK_SQR_HOT(R), PPP), fp_add_lazy<Q>(Qv, Qv));
     // Y3 = R (Q - X3) - Y1 PPP as ONE fused pair of products sharing their Montgomery reduction (200 instead of 272 MACs)
     fp_t Y3 = VK_MUL2_HOT(R, fp_sub_lazy<Q>(Qv, X3), fp_neg_lazy<Q>(acc.y), PPP);
     acc.x = X3;

@@ -390,6 +390,167 @@ template <class P>
 __host__ __device__ __noinline__ fp_t fp_mul2_lazy_ni(const fp_t a, const fp_t b, const fp_t c, const fp_t d) {
     return fp_mul2_lazy<P>(a, b, c, d);
 }
+// ---------------------------------------------------------------------------------------------
+// Dedicated squaring for the hot loops.  a^2 = sum_i a_i * V_i * 2^(32 i) with the row vectors
+//     V_i = [0 .. 0, a_i, d_(i+1) & ~1, d_(i+2), .. , d_7]      (d = 2a as an 8-limb number; a <= 2p < 2^255)
+// i.e. row i carries its diagonal term and the DOUBLED off-diagonal terms to its right ((2a) >> 32(i+1) equals
+// 2 (a >> 32(i+1)) + bit 31 of a_i: clearing bit 0 of d_(i+1) removes the stray bit).  Row i has 8 - i products instead
+// of 8 — 36 instead of 64 for the whole square — and is interleaved with the same reduction rows as fp_mul_lazy:
+// 36 + 64 + 8 = 108 multiply-accumulates instead of 136.  The running total obeys the bound of the fused pair
+// (t_i < t_(i-1) / 2^32 + 5p, V_i <= 4p), the result (a^2 + M p) / R < 4p^2 / R + p < 2p needs no subtraction.
+// ---------------------------------------------------------------------------------------------
+// pairs K0..3 of mad_row4 (the multiplicands of the pairs below K0 are zero)
+template <int K0>
+VK_HD void mad_row_from(uint32_t* acc, uint32_t& top, const uint32_t* m, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    if constexpr (K0 == 0) {
+        mad_row4(acc, top, m[0], m[1], m[2], m[3], b);
+    } else if constexpr (K0 == 1) {
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, %6, 0;"
+            : "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(b));
+    } else if constexpr (K0 == 2) {
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, %4, 0;"
+            : "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(m[2]), "r"(m[3]), "r"(b));
+    } else if constexpr (K0 == 3) {
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, %2, 0;"
+            : "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(m[3]), "r"(b));
+    }
+#else
+    uint32_t c = 0;
+    for (int k = K0; k < 4; ++k) host_mad_pair(acc[2 * k], acc[2 * k + 1], m[k], b, acc[2 * k], acc[2 * k + 1], c);
+    top += c;
+#endif
+}
+
+// shift_mad_row4 whose pairs below K0 have zero multiplicands: those pairs only pass e[] (and the carry) on
+template <int K0>
+VK_HD void shift_mad_row_from(uint32_t& x0, uint32_t* y, const uint32_t* e, const uint32_t* m, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    if constexpr (K0 == 0) {
+        shift_mad_row4(x0, y, e, m[0], m[1], m[2], m[3], b);
+    } else if constexpr (K0 == 1) {
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %10, 0;\n\t"
+            "addc.cc.u32 %2, %11, 0;\n\t"
+            "madc.lo.cc.u32 %3, %16, %19, %12;\n\t"
+            "madc.hi.cc.u32 %4, %16, %19, %13;\n\t"
+            "madc.lo.cc.u32 %5, %17, %19, %14;\n\t"
+            "madc.hi.cc.u32 %6, %17, %19, %15;\n\t"
+            "madc.lo.cc.u32 %7, %18, %19, 0;\n\t"
+            "madc.hi.u32 %8, %18, %19, 0;"
+            : "+r"(x0), "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7])
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(b));
+    } else if constexpr (K0 == 2) {
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %10, 0;\n\t"
+            "addc.cc.u32 %2, %11, 0;\n\t"
+            "addc.cc.u32 %3, %12, 0;\n\t"
+            "addc.cc.u32 %4, %13, 0;\n\t"
+            "madc.lo.cc.u32 %5, %16, %18, %14;\n\t"
+            "madc.hi.cc.u32 %6, %16, %18, %15;\n\t"
+            "madc.lo.cc.u32 %7, %17, %18, 0;\n\t"
+            "madc.hi.u32 %8, %17, %18, 0;"
+            : "+r"(x0), "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7])
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(m[2]), "r"(m[3]), "r"(b));
+    } else {
+        static_assert(K0 == 3, "row 7 is the last one");
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %10, 0;\n\t"
+            "addc.cc.u32 %2, %11, 0;\n\t"
+            "addc.cc.u32 %3, %12, 0;\n\t"
+            "addc.cc.u32 %4, %13, 0;\n\t"
+            "addc.cc.u32 %5, %14, 0;\n\t"
+            "addc.cc.u32 %6, %15, 0;\n\t"
+            "madc.lo.cc.u32 %7, %16, %17, 0;\n\t"
+            "madc.hi.u32 %8, %16, %17, 0;"
+            : "+r"(x0), "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]), "=r"(y[4]), "=r"(y[5]), "=r"(y[6]), "=r"(y[7])
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(m[3]), "r"(b));
+    }
+#else
+    uint64_t s = (uint64_t)x0 + e[1];
+    x0 = (uint32_t)s;
+    uint32_t c = (uint32_t)(s >> 32);
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = k < 3 ? e[2 * k + 2] : 0u, hi = k < 3 ? e[2 * k + 3] : 0u;
+        host_mad_pair(y[2 * k], y[2 * k + 1], k < K0 ? 0u : m[k], b, lo, hi, c);
+    }
+#endif
+}
+
+// limb j of the row vector V_I (see above); zero below the diagonal
+template <int I>
+VK_HD uint32_t sqr_row_limb(const uint32_t* a, const uint32_t* d, int j) {
+    return j < I ? 0u : j == I ? a[I] : j == I + 1 ? (d[j] & ~1u) : d[j];
+}
+// row I >= 1 of the square: x = the array that becomes column-0 aligned, e = the previous column-0 array, y = the new column-1 array
+template <class P, int I>
+VK_HD void sqr_row(uint32_t* x, const uint32_t* e, uint32_t* y, const uint32_t* a, const uint32_t* d) {
+    uint32_t me[4], mo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        me[k] = sqr_row_limb<I>(a, d, 2 * k);
+        mo[k] = sqr_row_limb<I>(a, d, 2 * k + 1);
+    }
+    shift_mad_row_from<I / 2>(x[0], y, e, mo, a[I]);
+    if constexpr (I < 7) mad_row_from<(I + 1) / 2>(x, y[7], me, a[I]);
+    reduce_step<P>(x, y);
+}
+// a^2 R^-1 mod p in [0, 2p) for a in [0, 2p]
+template <class P>
+VK_HD fp_t fp_sqr_lazy(const fp_t& a) {
+    uint32_t d[8], u[8], v[8], y[8];
+#pragma unroll
+    for (int k = 7; k > 0; --k) d[k] = (a.l[k] << 1) | (a.l[k - 1] >> 31);
+    d[0] = a.l[0] << 1;
+    // row 0: V_0 = [a0, d1 & ~1, d2 .. d7] times a0
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        uint64_t t0 = (uint64_t)sqr_row_limb<0>(a.l, d, j) * a.l[0];
+        uint64_t t1 = (uint64_t)sqr_row_limb<0>(a.l, d, j + 1) * a.l[0];
+        u[j] = (uint32_t)t0;
+        u[j + 1] = (uint32_t)(t0 >> 32);
+        v[j] = (uint32_t)t1;
+        v[j + 1] = (uint32_t)(t1 >> 32);
+    }
+    reduce_step<P>(u, v);
+#define VK_SQR_ROWS(I, X, E)                 \
+    sqr_row<P, I>(X, E, y, a.l, d);          \
+    _Pragma("unroll") for (int k = 0; k < 8; ++k) E[k] = y[k];
+    VK_SQR_ROWS(1, v, u)
+    VK_SQR_ROWS(2, u, v)
+    VK_SQR_ROWS(3, v, u)
+    VK_SQR_ROWS(4, u, v)
+    VK_SQR_ROWS(5, v, u)
+    VK_SQR_ROWS(6, u, v)
+    VK_SQR_ROWS(7, v, u)
+#undef VK_SQR_ROWS
+    uint32_t vs[8];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) vs[k] = v[k + 1];
+    vs[7] = 0;
+    fp_t r;
+    add8(r.l, u, vs);
+    return r;
+}
+template <class P>
+__host__ __device__ __noinline__ fp_t fp_sqr_lazy_ni(const fp_t a) {
+    return fp_sqr_lazy<P>(a);
+}
 // 2p - a for a in [0, 2p): the negation of a lazy value, in (0, 2p]
 template <class P>
 VK_HD fp_t fp_neg_lazy(const fp_t& a) {

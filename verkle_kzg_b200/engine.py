@@ -445,6 +445,10 @@ class Engine:
                                           ctypes.c_uint32(iters), ctypes.byref(macs)), "vkzg_probe_imad_dev")
         return macs.value
 
+    def probe_fq_sqr_dev(self, d_x, n, iters, mode=0):
+        check(self._L.vkzg_probe_fq_sqr_dev(self._ctx, dptr(d_x), ctypes.c_uint64(n), ctypes.c_uint32(iters), ctypes.c_uint32(mode)),
+              "vkzg_probe_fq_sqr_dev")
+
     def probe_fq_mul_dev(self, d_x, d_y, n, iters):
         check(self._L.vkzg_probe_fq_mul_dev(self._ctx, dptr(d_x), dptr(d_y), ctypes.c_uint64(n), ctypes.c_uint32(iters)),
               "vkzg_probe_fq_mul_dev")
