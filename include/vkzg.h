@@ -150,6 +150,13 @@ int32_t vkzg_kzg_commit_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr
                                    const vkzg_fr* points, uint64_t B, vkzg_g1_affine* commitments, vkzg_g1_affine* proof,
                                    vkzg_fr* y);
 
+/* KZG::prove_all_points (kzg/mod.rs:200-235): every vector opened at ALL Dn points of its data domain — proof[B][Dn],
+ * y[B][Dn], with proof[b][i] == KZG::prove_point(f_b, i) and y[b][i] = f_b[i] (0 for len <= i < Dn).  The reference's
+ * function is private dead code that stops at Feist-Khovratovich's h-vector and panics on data[i], i >= N; its contract
+ * (what its unregistered test checks: every entry verifies as a single-point proof) is what this entry keeps.          */
+int32_t vkzg_kzg_prove_all_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f /*[B][len]*/, uint32_t len, uint32_t domain_n,
+                                 uint64_t B, vkzg_g1_affine* proof /*[B][Dn]*/, vkzg_fr* y /*[B][Dn]*/);
+
 /* ---- I1: IPA::prove_point + low_level_ipa (ipa/mod.rs:137-154, :268-319), batched -------------------- */
 /* a[B][N], points[B], commitments[B].  `prefix` (may be NULL) is the byte state of an in-flight transcript
  * shared by all B proofs (lib.rs:127-133 / multiproof.rs:174), `dst` the transcript's domain label

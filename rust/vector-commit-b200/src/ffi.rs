@@ -38,6 +38,8 @@ extern "C" {
     pub fn vkzg_to_data_item(ctx: *mut vkzg_ctx, points: *const vkzg_g1_affine, n: u64, out: *mut vkzg_fr) -> i32;
     pub fn vkzg_kzg_open_batch(ctx: *mut vkzg_ctx, key_id: u32, f: *const vkzg_fr, len: u32, domain_n: u32, points: *const vkzg_fr,
                                b: u64, proof: *mut vkzg_g1_affine, y: *mut vkzg_fr) -> i32;
+    pub fn vkzg_kzg_prove_all_batch(ctx: *mut vkzg_ctx, key_id: u32, f: *const vkzg_fr, len: u32, domain_n: u32, b: u64,
+                                    proof: *mut vkzg_g1_affine, y: *mut vkzg_fr) -> i32;
     pub fn vkzg_kzg_commit_open_batch(ctx: *mut vkzg_ctx, key_id: u32, f: *const vkzg_fr, len: u32, domain_n: u32, points: *const vkzg_fr,
                                       b: u64, commitments: *mut vkzg_g1_affine, proof: *mut vkzg_g1_affine, y: *mut vkzg_fr) -> i32;
     pub fn vkzg_ipa_prove_batch(ctx: *mut vkzg_ctx, key_id: u32, a: *const vkzg_fr, points: *const vkzg_fr,

@@ -322,6 +322,22 @@ impl GpuKzg {
             _ => Err(KZGError::OutOfCRS),
         }
     }
+    /// kzg/mod.rs:200-235 (`prove_all_points`, unreachable in the reference): one opening per point of the data's domain,
+    /// entry i equal to `prove_point(key, i, data)` -> vkzg_kzg_prove_all_batch (B = 1)
+    pub fn prove_all_points(key: &GpuKzgParams, data: &LagrangeBasis<Fr, D>) -> Result<Vec<KZGProof<Fr, G1Projective>>, KZGError> {
+        let ev = data.elements_ref();
+        let dn = data.domain_size().max(ev.len()).next_power_of_two();
+        let mut pf = vec![vkzg_g1_affine::default(); dn];
+        let mut y = vec![Fr::zero(); dn];
+        let st = unsafe {
+            vkzg_kzg_prove_all_batch(key.gpu.ctx, key.gpu.id, fr_ptr(ev), ev.len() as u32, data.domain_size() as u32, 1, pf.as_mut_ptr(),
+                                     y.as_mut_ptr() as *mut vkzg_fr)
+        };
+        match st {
+            0 => Ok(pf.iter().zip(y).map(|(p, y)| KZGProof { proof: from_abi(p), y }).collect()),
+            _ => Err(KZGError::OutOfCRS),
+        }
+    }
     /// kzg/mod.rs:165-189: unchanged host pairing check
     pub fn verify_point(key: &GpuKzgParams, commitment: &G1Projective, point: Fr, proof: &KZGProof<Fr, G1Projective>) -> Result<bool, KZGError> {
         crate::kzg::KZG::<Bn254, H, D>::verify_point(&key.inner, commitment, point, proof, None)

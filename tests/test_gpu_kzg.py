@@ -177,3 +177,46 @@ def test_kzg_setup_from_secret_edge_cases(eng):
     for t, m in ((pow(w32, 5, orc.R_MOD), 20), (pow(w32, 5, orc.R_MOD), 32), (0, 9), (1, 16), (1, 11)):
         assert (eng.kzg_setup_from_secret(gkey, orc.fr_to_buf([t])[0], m) == orc.kzg_setup(m, t)).all(), (t, m)
     gkey.free()
+
+
+@pytest.mark.parametrize("N,length,domain,wb,B", [(16, 8, 16, 8, 3), (32, 20, 0, 8, 2), (256, 256, 0, 0, 2), (64, 64, 0, 8, 300)])
+def test_prove_all_points(eng, N, length, domain, wb, B):
+    """KZG::prove_all_points (kzg/mod.rs:200-235) by its contract — the shape of the reference's unregistered test_amortized_proof
+    (kzg/mod.rs:298-308): entry i is the single-point proof at i.  Checked against the oracle's prove_point, the tau = 100
+    pairing-free verification, and (B = 300: several 1 GiB pieces would need B > 4096 at this width, so one piece) the batched
+    single-point entry."""
+    srs, key = _key(eng, N, wb)
+    rng = np.random.default_rng(N + length + B)
+    f = orc.rand_fr_buf(rng, B * length).reshape(B, length, 32)
+    want = domain if domain else length
+    dn = 1
+    while dn < want:
+        dn <<= 1
+    proof, y = eng.kzg_prove_all_batch(key, f, domain_n=domain)
+    assert proof.shape == (B, dn, 64) and y.shape == (B, dn, 32)
+    idx = orc.fr_to_buf(list(range(dn)))
+    rows = range(B) if B <= 3 else (0, B // 2, B - 1)
+    C = eng.commit_batch(key, f)
+    for b in rows:
+        pf1, y1 = eng.kzg_open_batch(key, np.repeat(f[b:b + 1], dn, axis=0), idx, domain_n=domain)
+        assert (proof[b] == pf1).all() and (y[b] == y1).all()
+        for i in range(dn):
+            assert (y[b, i] == (f[b, i] if i < length else 0)).all()
+            eq = orc.divide_by_vanishing(N, f[b], want, i)
+            if dn <= 32 or i in (0, 1, dn // 2, dn - 1):
+                assert (proof[b, i] == orc.msm(srs, eq)).all(), (b, i)
+                if dn == N:
+                    assert orc.kzg_verify_tau(srs, TAU, C[b], idx[i], proof[b, i], y[b, i]), (b, i)
+    if B > 3:   # every row against the batched single-point path
+        pf_all, y_all = eng.kzg_open_batch(key, np.repeat(f, dn, axis=0), np.tile(idx, (B, 1)), domain_n=domain)
+        assert (proof.reshape(-1, 64) == pf_all).all() and (y.reshape(-1, 32) == y_all).all()
+    key.free()
+
+
+def test_prove_all_points_errors(eng):
+    srs, key = _key(eng, 16, 8)
+    f = orc.rand_fr_buf(np.random.default_rng(3), 2 * 20).reshape(2, 20, 32)
+    from verkle_kzg_b200._lib import VkzgError
+    with pytest.raises(VkzgError):
+        eng.kzg_prove_all_batch(key, f)          # rows longer than the key
+    key.free()

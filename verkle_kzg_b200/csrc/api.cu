@@ -178,11 +178,13 @@ int32_t vkzg_key_load_dev(vkzg_ctx* ctx, const vkzg_g1_affine* d_bases, uint32_t
     if (kind == VKZG_KEY_MSM && d_q) return VKZG_ERR_ARG;
     uint32_t c = window_bits;
     // MSM keys: the weighted bucket sum is a latency-bound tail whose cost grows with the 2^(c-1) buckets, the bucket pass with
-    // the ceil(255/c) digits per scalar.  Measured on B200 (profiles/r02_msm_window_sweep.txt): c = 17 (15 digits, running-sum
-    // tail) from 2^20 points on, c = 15 (17 digits, bit-parallel tail) for 2^17 .. 2^19 — the slices of a sharded MSM —,
-    // c = 13 below.  (c = 14 leaves a 2-bit top window: four buckets receive a quarter of all scalars each — correct but
-    // ~20x slower; never the default.)
-    if (c == 0) c = kind == VKZG_KEY_WINDOW ? 16 : (n >= (1u << 20) ? 17 : (n >= (1u << 17) ? 15 : (n >= (1u << 14) ? 13 : 12)));
+    // the ceil(255/c) digits per scalar.  Measured on B200 (profiles/r02_msm_window_sweep.txt, profiles/r02_msm_tail_sweep.txt):
+    // with the two-level tail c = 17 (15 digits) from 2^19 points on, 16 at 2^18, 15 at 2^17 — the slices of a sharded MSM —,
+    // c = 13 below.  (A width whose TOP window is only a few bits wide — c = 14, 18, 19 — sends a large share of all scalars
+    // into a handful of buckets: correct but 20-250x slower; never the default.)
+    if (c == 0)
+        c = kind == VKZG_KEY_WINDOW ? 16
+            : (n >= (1u << 19) ? 17 : (n >= (1u << 18) ? 16 : (n >= (1u << 17) ? 15 : (n >= (1u << 14) ? 13 : 12))));
     if (kind == VKZG_KEY_MSM && window_bits == 0 && getenv("VKZG_MSM_C")) c = (uint32_t)atoi(getenv("VKZG_MSM_C"));  // measurement knob
     if (c < 2 || c > 20) return VKZG_ERR_ARG;
     k.c = c;

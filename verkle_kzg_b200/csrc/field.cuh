@@ -551,6 +551,13 @@ template <class P>
 __host__ __device__ __noinline__ fp_t fp_sqr_lazy_ni(const fp_t a) {
     return fp_sqr_lazy<P>(a);
 }
+// canonical square (a <= 2p in, [0, p) out) through the dedicated square
+template <class P>
+VK_HD fp_t fp_sqr(const fp_t& a) {
+    fp_t r = fp_sqr_lazy<P>(a);
+    fp_cond_sub_p<P>(r.l, 0);
+    return r;
+}
 // 2p - a for a in [0, 2p): the negation of a lazy value, in (0, 2p]
 template <class P>
 VK_HD fp_t fp_neg_lazy(const fp_t& a) {
@@ -605,10 +612,6 @@ VK_HD bool fp_is_zero_lazy(const fp_t& a) {
     return z == 0 || e == 0;
 }
 
-template <class P>
-VK_HD fp_t fp_sqr(const fp_t& a) {
-    return fp_mul<P>(a, a);
-}
 
 template <class P>
 VK_HD fp_t fp_add(const fp_t& a, const fp_t& b) {

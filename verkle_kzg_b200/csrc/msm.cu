@@ -67,19 +67,36 @@ __global__ void __launch_bounds__(256) k_msm_scatter_fixed(const fp_t* __restric
     fp_t k = fp_from_mont<S>(fp_load_ro(scalars + i));
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0, lost = 0;
-    for (uint32_t w = 0; w < W; ++w) {
-        uint32_t v = scalar_bits(k.l, w * c, c) + carry;
-        uint32_t neg = v >= half && w + 1 < W ? 1u : 0u;
-        uint32_t mag = neg ? (1u << c) - v : v;
-        carry = neg;
-        if (mag) {
-            uint32_t b = mag - 1;
-            uint32_t pos = atomicAdd(cursor + b, 1u);
-            if (pos < cap + (b < top_n ? top_extra : 0u))
-                entries[msm_list_base(b, cap, top_n, top_extra) + pos] = (uint32_t)((uint64_t)w * key_n + first + i) | (neg << 31);
-            else
-                ++lost;
+    // four digits at a time: their atomics are issued back to back (four cursor round trips in flight per thread), then the
+    // four entry stores (measured at 2^20 points: see DESIGN.md, MSM flow)
+    for (uint32_t w0 = 0; w0 < W; w0 += 4) {
+        uint32_t b[4], ent[4], pos[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t w = w0 + j;
+            b[j] = 0xffffffffu;
+            if (w < W) {
+                uint32_t v = scalar_bits(k.l, w * c, c) + carry;
+                uint32_t neg = v >= half && w + 1 < W ? 1u : 0u;
+                uint32_t mag = neg ? (1u << c) - v : v;
+                carry = neg;
+                if (mag) {
+                    b[j] = mag - 1;
+                    ent[j] = (uint32_t)((uint64_t)w * key_n + first + i) | (neg << 31);
+                }
+            }
         }
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (b[j] != 0xffffffffu) pos[j] = atomicAdd(cursor + b[j], 1u);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (b[j] != 0xffffffffu) {
+                if (pos[j] < cap + (b[j] < top_n ? top_extra : 0u))
+                    entries[msm_list_base(b[j], cap, top_n, top_extra) + pos[j]] = ent[j];
+                else
+                    ++lost;
+            }
     }
     if (lost) atomicAdd(dropped, lost);
 }
@@ -183,7 +200,14 @@ __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restric
 static const int BS_THREADS = 128;
 static const int BS_SLICE = 512;   // buckets per CTA (4 warps: one per sub-partition, so the dependent additions do not share a multiplier pipe)
 
+// weight of element e: plain bucket sets weigh b + 1; the group sums of the two-level form (split_h != 0) weigh
+// e * l for the h per-group sums S_e (e < split_h) and (e - split_h) + 1 for the l per-position sums T_(e - split_h)
+__device__ __forceinline__ uint32_t msm_weight(uint32_t e, uint32_t split_h, uint32_t l) {
+    return split_h == 0 ? e + 1 : (e < split_h ? e * l : e - split_h + 1);
+}
+
 __global__ void __launch_bounds__(BS_THREADS) k_msm_bitsums(const xyzz_t* __restrict__ buckets, uint32_t nb, uint32_t slices,
+                                                            uint32_t split_h, uint32_t split_l,
                                                             xyzz_t* __restrict__ out /*[bits][slices]*/) {
     __shared__ xyzz_t sh[BS_THREADS / 32];
     const uint32_t bit = blockIdx.y, slice = blockIdx.x;
@@ -192,7 +216,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_msm_bitsums(const xyzz_t* __rest
 #pragma unroll 1
     for (uint32_t i = threadIdx.x; i < BS_SLICE; i += BS_THREADS) {
         uint32_t b = lo + i;
-        if (b < nb && (((b + 1) >> bit) & 1)) {
+        if (b < nb && ((msm_weight(b, split_h, split_l) >> bit) & 1)) {
             xyzz_t B;
             B.x = fp_load(&buckets[b].x);
             B.y = fp_load(&buckets[b].y);
@@ -255,6 +279,44 @@ __global__ void __launch_bounds__(32) k_msm_bitcombine(const xyzz_t* __restrict_
 #pragma unroll 1
     for (int off = 1; off < 32; off <<= 1) t = xyzz_add_pair(t, off);
     if (lane == 0) out[0] = t;
+}
+
+// ---- two-level form for large bucket sets: with b = hi * l + lo (h groups of l buckets),
+//          sum_b (b + 1) B_b = l * sum_hi hi S_hi + sum_lo (lo + 1) T_lo ,   S_hi = sum_lo B_(hi,lo) ,  T_lo = sum_hi B_(hi,lo)
+//      — 2 nb additions like the running sums, but as h + l independent PLAIN sums (one CTA each: one addition per thread pair,
+//      a pair-split shuffle tree, a shared-memory level), followed by the bit-parallel weighted sum above over only h + l
+//      elements.  Depth ~10 + ~30 dependent operations instead of ~45 full additions on 64 warps, and the bulk of the
+//      work runs at full occupancy.
+static const int GS_THREADS = 128;
+__global__ void __launch_bounds__(GS_THREADS) k_msm_group_sums(const xyzz_t* __restrict__ buckets, uint32_t h, uint32_t l,
+                                                               xyzz_t* __restrict__ out /*[h + l]*/) {
+    __shared__ xyzz_t sh[GS_THREADS / 32];
+    const uint32_t g = blockIdx.x;
+    const bool row = g < h;                       // S_g: l consecutive buckets; else T_(g - h): h buckets, stride l
+    const uint32_t cnt = row ? l : h;
+    const size_t base = row ? (size_t)g * l : (size_t)(g - h);
+    const size_t stride = row ? 1 : l;
+    xyzz_t acc = xyzz_inf();
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < cnt; i += GS_THREADS) {
+        const xyzz_t* src = buckets + base + (size_t)i * stride;
+        xyzz_t B;
+        B.x = fp_load(&src->x);
+        B.y = fp_load(&src->y);
+        B.zz = fp_load(&src->zz);
+        B.zzz = fp_load(&src->zzz);
+        acc = xyzz_add_ni(acc, B);
+    }
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) acc = xyzz_add_pair(acc, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        xyzz_t v = threadIdx.x < GS_THREADS / 32 ? sh[threadIdx.x] : xyzz_inf();
+#pragma unroll 1
+        for (int off = 1; off < GS_THREADS / 32; off <<= 1) v = xyzz_add_pair(v, off);
+        if (threadIdx.x == 0) out[g] = v;
+    }
 }
 
 // ---- running-sum form of the weighted bucket sum: less work (2 additions per bucket), longer chain — used for large bucket
@@ -396,17 +458,35 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     }
     VK_TRY(launch_check(ctx));
     uint32_t rblocks;
-    static int bitpar_max = -1;
+    static int bitpar_max = -1, tail_form = -1;
     if (bitpar_max < 0) {
         const char* e = getenv("VKZG_MSM_BITPAR_MAX");
-        bitpar_max = e ? atoi(e) : 16384;
+        bitpar_max = e ? atoi(e) : 4096;
+        e = getenv("VKZG_MSM_TAIL");  // measurement knob: 1 = bit-parallel, 2 = running sums, 3 = two-level; default by size
+        tail_form = e ? atoi(e) : 0;
     }
-    if (nb <= (uint32_t)bitpar_max) {
-        // measured at n = 2^16 (B200): c = 16 / running sums 325 us for this tail; c = 13 / bit-parallel see DESIGN.md
-        const uint32_t bits = k.c, slices = (nb + BS_SLICE - 1) / BS_SLICE;  // weights 1 .. 2^(c-1): c bits
+    int form = tail_form ? tail_form : (nb <= (uint32_t)bitpar_max ? 1 : 3);
+    if (form == 3 && k.c < 5) form = 1;
+    DevBuf<xyzz_t> groups;
+    if (form == 1 || form == 3) {
+        const xyzz_t* elems = buckets;
+        uint32_t n_el = nb, bits = k.c, split_h = 0, split_l = 0;  // weights 1 .. 2^(c-1): c bits
+        if (form == 3) {
+            const uint32_t lg = k.c - 1;
+            split_h = 1u << ((lg + 1) / 2);
+            split_l = nb / split_h;
+            n_el = split_h + split_l;
+            VK_TRY(groups.alloc(ctx, n_el));
+            k_msm_group_sums<<<n_el, GS_THREADS, 0, s>>>(buckets, split_h, split_l, groups);
+            VK_TRY(launch_check(ctx));
+            elems = groups;
+            bits = lg;                                  // weights (h - 1) l < 2^(c-1) and l <= 2^((c-1)/2)
+            while ((split_l >> bits) != 0) ++bits;      // (c - 1 = 1: l = 1 needs its own bit)
+        }
+        const uint32_t slices = (n_el + BS_SLICE - 1) / BS_SLICE;
         rblocks = bits * slices;
         VK_TRY(partial.alloc(ctx, (size_t)rblocks + 1 + bits));
-        k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(buckets, nb, slices, partial);
+        k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(elems, n_el, slices, split_h, split_l, partial);
         VK_TRY(launch_check(ctx));
         k_msm_bitcombine<<<bits, 32, 0, s>>>(partial, bits, slices, partial.p + rblocks + 1, counts.p + nb + 1, partial.p + rblocks);
         VK_TRY(launch_check(ctx));

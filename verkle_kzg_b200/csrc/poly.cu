@@ -30,9 +30,10 @@ __device__ __forceinline__ fp_t warp_sum_fr2(fp_t v) {
 }
 
 struct PolyArgs {
-    const fp_t* f;       // [B][len]
-    const fp_t* points;  // [B]
+    const fp_t* f;       // [B / share][len]
+    const fp_t* points;  // [B], or nullptr: opening p is at the in-domain index p % share
     uint64_t B;
+    uint32_t share;      // consecutive openings per data row (1: a row per opening; Dn: all in-domain openings of each row)
     uint32_t len, Dn;    // data row length, data domain size
     uint32_t N, Np;      // key size, key domain size
     const fp_t *wD, *wD_inv, *dD_inv;  // data-domain tables
@@ -48,9 +49,9 @@ __global__ void __launch_bounds__(128) k_poly(PolyArgs A) {
     uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (p >= A.B) return;
-    const fp_t* f = A.f + p * A.len;
+    const fp_t* f = A.f + (A.share > 1 ? p / A.share : p) * A.len;
     fp_t* row = A.q ? A.q + p * A.Dn : A.scratch + p * A.len;
-    const fp_t z = fp_load_ro(A.points + p);
+    const fp_t z = A.points ? fp_load_ro(A.points + p) : fp_from_u32<S>((uint32_t)(p % A.share));
     const fp_t zc = fp_from_mont<S>(z);
     const bool small = (zc.l[1] | zc.l[2] | zc.l[3] | zc.l[4] | zc.l[5] | zc.l[6] | zc.l[7]) == 0;
     const uint32_t zi = zc.l[0];
@@ -165,7 +166,7 @@ static int32_t data_domain(vkzg_ctx* ctx, const Key& k, uint32_t len, uint32_t d
 
 // q == nullptr: evaluate only.  Returns VKZG_ERR_RANGE (after synchronising) if check_err and a row panicked.
 int32_t poly_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points, uint64_t B,
-                   fp_t* d_q, fp_t* d_y, bool check_err) {
+                   fp_t* d_q, fp_t* d_y, bool check_err, uint32_t share) {
     if (B == 0) return VKZG_OK;
     if (len == 0 || len > k.n) return VKZG_ERR_RANGE;
     uint32_t Dn;
@@ -181,6 +182,7 @@ int32_t poly_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, u
     A.f = d_f;
     A.points = d_points;
     A.B = B;
+    A.share = share ? share : 1;
     A.len = len;
     A.Dn = Dn;
     A.N = k.n;
@@ -346,6 +348,44 @@ int32_t vkzg_kzg_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, ui
     VK_TRY(kzg_open_core(ctx, *k, df, len, domain_n, dp, B, dpr, dy, true));
     VK_TRY(download(ctx, proof, dpr.p, B));
     VK_TRY(download(ctx, y, dy.p, B));
+    return stream_sync(ctx);
+}
+
+// KZG::prove_all_points (kzg/mod.rs:200-235): the openings of every vector at ALL points of its data domain.  The reference's
+// function is unreachable (private, its test is not registered), stops after the h-vector of Feist-Khovratovich (no final FFT)
+// and indexes data[i] for i up to 2N - 1; what is reproduced is its contract — proof[b][i] == prove_point(f_b, i), y[b][i] = f_b[i].
+// With the window tables an opening is Dn x W table additions: Dn openings of a width-256 row cost the same field products as
+// FK's ~3800 variable-base scalar multiplications (two size-2Dn group FFTs + the Hadamard product), so the all-points prover is
+// the batched single-point path with the data row shared by Dn consecutive openings, cut into pieces of <= 1 GiB of quotients.
+int32_t vkzg_kzg_prove_all_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* f, uint32_t len, uint32_t domain_n, uint64_t B,
+                                 vkzg_g1_affine* proof, vkzg_fr* y) {
+    VK_TRY(ctx_check(ctx));
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_WINDOW || (B && (!f || !proof || !y))) return VKZG_ERR_ARG;
+    if (len == 0 || len > k->n) return VKZG_ERR_RANGE;
+    if (domain_n && domain_n < len) return VKZG_ERR_ARG;
+    const uint32_t Dn = data_domain_size(len, domain_n);
+    if (Dn > k->n) return VKZG_ERR_UNSUPPORTED;
+    if (B == 0) return VKZG_OK;
+    uint64_t piece = (1ull << 30) / ((uint64_t)Dn * Dn * sizeof(fp_t));
+    if (piece == 0) piece = 1;
+    if (piece > B) piece = B;
+    DevBuf<fp_t> df, dq, dy;
+    DevBuf<xyzz_t> acc;
+    DevBuf<affine_t> dpr;
+    VK_TRY(upload(ctx, df, f, B * len));
+    VK_TRY(dq.alloc(ctx, piece * Dn * Dn));
+    VK_TRY(dy.alloc(ctx, B * Dn));
+    VK_TRY(acc.alloc(ctx, piece * Dn));
+    VK_TRY(dpr.alloc(ctx, B * Dn));
+    for (uint64_t b0 = 0; b0 < B; b0 += piece) {
+        const uint64_t nb = B - b0 < piece ? B - b0 : piece;
+        VK_TRY(poly_batch(ctx, *k, df.p + b0 * len, len, domain_n, nullptr, nb * Dn, dq, dy.p + b0 * Dn, false, Dn));
+        VK_TRY(fixed_base_msm(ctx, *k, dq, Dn, nb * Dn, 0, 0xffffffffu, acc));
+        VK_TRY(normalize_points(ctx, acc, nb * Dn, dpr.p + b0 * Dn));
+    }
+    VK_TRY(download(ctx, proof, dpr.p, B * Dn));
+    VK_TRY(download(ctx, y, dy.p, B * Dn));
     return stream_sync(ctx);
 }
 

@@ -257,7 +257,7 @@ int32_t ipa_verify_core(vkzg_ctx* ctx, const Key& k, int mode, const fp_t* d_poi
                         uint32_t prefix_len, const char* dst, const affine_t* d_L, const affine_t* d_R, const fp_t* d_tip,
                         const fp_t* d_y, int32_t* d_ok);
 int32_t poly_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points, uint64_t B,
-                   fp_t* d_q, fp_t* d_y, bool check_err);
+                   fp_t* d_q, fp_t* d_y, bool check_err, uint32_t share = 1);
 int32_t kzg_open_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points,
                       uint64_t B, affine_t* d_proof, fp_t* d_y, bool check_err);
 int32_t var_base_msm(vkzg_ctx* ctx, const affine_t* d_points, const fp_t* d_scalars, uint64_t n, affine_t* d_out);

@@ -306,6 +306,17 @@ class Engine:
               "vkzg_kzg_commit_open_batch")
         return C, proof, y
 
+    def kzg_prove_all_batch(self, key, f, domain_n=0):
+        """KZG::prove_all_points (kzg/mod.rs:200-235): f [B,len,32] -> (proof [B,Dn,64], y [B,Dn,32]), Dn = the data domain size"""
+        f = u8(f, 32)
+        B, ln = f.shape[0], f.shape[1]
+        Dn = 1 << _log2(max(ln, domain_n))
+        proof = np.zeros((B, Dn, 64), dtype=np.uint8)
+        y = np.zeros((B, Dn, 32), dtype=np.uint8)
+        check(self._L.vkzg_kzg_prove_all_batch(self._ctx, ctypes.c_uint32(key.id), hptr(f), ctypes.c_uint32(ln), ctypes.c_uint32(domain_n),
+                                               ctypes.c_uint64(B), hptr(proof), hptr(y)), "vkzg_kzg_prove_all_batch")
+        return proof, y
+
     def kzg_open_batch_dev(self, key, d_f, ln, d_points, B, d_proof, d_y, domain_n=0):
         check(self._L.vkzg_kzg_open_batch_dev(self._ctx, ctypes.c_uint32(key.id), dptr(d_f), ctypes.c_uint32(ln),
                                               ctypes.c_uint32(domain_n), dptr(d_points),

@@ -263,6 +263,12 @@ class KZG(_Scheme):
         return dict(proof=proof, y=y)
 
     @staticmethod
+    def prove_all_points(key, data):
+        """kzg/mod.rs:200-235: the opening at every point of the data's domain, entry i equal to prove_point(key, _, i, data)"""
+        proof, y = key.engine.kzg_prove_all_batch(key.key, data.evaluations.reshape(1, -1, 32), domain_n=data.domain_n)
+        return [dict(proof=p, y=v) for p, v in zip(proof[0], y[0])]
+
+    @staticmethod
     def verify_point(key, commitment, point, proof, transcript=None):
         raise NotImplementedError(
             "KZG::verify_point is two pairings (kzg/mod.rs:165-189); it stays on the host arkworks side of the "
