@@ -864,6 +864,9 @@ def measure(ctx, wl, c, steps, warmup, sampler=None, cpu=True):
             "achieved": achieved, "peak": peak, "unit": "TMAC32/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": "measured live: dependency-free mad.wide.u32 chains on all SMs (vkzg_probe_imad_dev); MEASURED_PEAKS.json has no integer figure",
             "work_model": f"{madds} mixed additions per unit x {FQ_MUL_PER_MADD} Fq-mul x {MAC32_PER_FQ_MUL} MAC32",
+            # what the kernel actually issues per mixed addition: 6 general products (136), 2 dedicated squares (108) and one
+            # fused pair sharing its reduction (200) = 1232 multiply-accumulates for the 1360 of the accounting above
+            "executed_mac32_per_addition": 6 * 136 + 2 * 108 + 200,
             "survey_accounting": survey_acct,
             "kernel_launches_timed": kn, "kernel_ms_total": kms, "kernel_share_of_step": kms / ms_k if ms_k else None,
             "one_stream_ms_per_step": ms_k / steps,

@@ -135,15 +135,50 @@ __global__ void __launch_bounds__(256) k_msm_clear_if(uint32_t* __restrict__ cou
     if (i < n) counts[i] = 0;
 }
 
+// Buckets in order of decreasing list length (single CTA: shared-memory histogram of the sizes, scan, scatter).  The lanes of
+// a warp serve 32 / P buckets and wait for the longest of their lists (sizes ~ Poisson: +-2 additions on 30 per lane at
+// n = 2^20, c = 17); with neighbours of equal size that wait disappears, and the longest lists start first.
+static const int ORD_BINS = 2048;
+__global__ void __launch_bounds__(1024) k_msm_order(const uint32_t* __restrict__ sizes, uint32_t nb, uint32_t* __restrict__ order) {
+    __shared__ uint32_t hist[ORD_BINS];
+    __shared__ uint32_t part[1024];
+    for (uint32_t i = threadIdx.x; i < ORD_BINS; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += 1024) {
+        uint32_t sz = sizes[b];
+        atomicAdd(&hist[ORD_BINS - 1 - (sz < ORD_BINS ? sz : ORD_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    const uint32_t h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1];
+    part[threadIdx.x] = h0 + h1;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const uint32_t base = part[threadIdx.x] - (h0 + h1);
+    hist[2 * threadIdx.x] = base;
+    hist[2 * threadIdx.x + 1] = base + h0;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += 1024) {
+        uint32_t sz = sizes[b];
+        order[atomicAdd(&hist[ORD_BINS - 1 - (sz < ORD_BINS ? sz : ORD_BINS - 1)], 1u)] = b;
+    }
+}
+
 // P (power of two <= 32) adjacent lanes per bucket
 __global__ void __launch_bounds__(128, 4) k_msm_bucket(const affine_t* __restrict__ table, const uint32_t* __restrict__ offsets,
                                                     const uint32_t* __restrict__ entries, uint32_t nb, uint32_t P, uint32_t cap,
                                                     uint32_t top_n, uint32_t top_extra, xyzz_t* __restrict__ buckets,
-                                                    const uint32_t* __restrict__ gate, uint32_t gate_want) {
+                                                    const uint32_t* __restrict__ gate, uint32_t gate_want,
+                                                    const uint32_t* __restrict__ order) {
     if (gate && (*gate != 0) != (gate_want != 0)) return;
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t b = (uint32_t)(t / P), p = (uint32_t)(t % P);
     bool live = b < nb;
+    if (live && order) b = __ldg(order + b);
     size_t lo = 0, hi = 0;
     if (live) {
         if (cap) {  // fixed-capacity layout: offsets[] holds the bucket sizes
@@ -287,10 +322,10 @@ __global__ void __launch_bounds__(32) k_msm_bitcombine(const xyzz_t* __restrict_
 //      a pair-split shuffle tree, a shared-memory level), followed by the bit-parallel weighted sum above over only h + l
 //      elements.  Depth ~10 + ~30 dependent operations instead of ~45 full additions on 64 warps, and the bulk of the
 //      work runs at full occupancy.
-static const int GS_THREADS = 128;
+static const int GS_THREADS = 64;   // (measured at 2^17 .. 2^20 points: 64 threads per group sum beat 32 and 128 by 0.3 - 1 %)
 __global__ void __launch_bounds__(GS_THREADS) k_msm_group_sums(const xyzz_t* __restrict__ buckets, uint32_t h, uint32_t l,
                                                                xyzz_t* __restrict__ out /*[h + l]*/) {
-    __shared__ xyzz_t sh[GS_THREADS / 32];
+    __shared__ xyzz_t sh[4];  // up to 128 threads
     const uint32_t g = blockIdx.x;
     const bool row = g < h;                       // S_g: l consecutive buckets; else T_(g - h): h buckets, stride l
     const uint32_t cnt = row ? l : h;
@@ -298,7 +333,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_msm_group_sums(const xyzz_t* __r
     const size_t stride = row ? 1 : l;
     xyzz_t acc = xyzz_inf();
 #pragma unroll 1
-    for (uint32_t i = threadIdx.x; i < cnt; i += GS_THREADS) {
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
         const xyzz_t* src = buckets + base + (size_t)i * stride;
         xyzz_t B;
         B.x = fp_load(&src->x);
@@ -312,9 +347,9 @@ __global__ void __launch_bounds__(GS_THREADS) k_msm_group_sums(const xyzz_t* __r
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
-        xyzz_t v = threadIdx.x < GS_THREADS / 32 ? sh[threadIdx.x] : xyzz_inf();
+        xyzz_t v = threadIdx.x < blockDim.x / 32 ? sh[threadIdx.x] : xyzz_inf();
 #pragma unroll 1
-        for (int off = 1; off < GS_THREADS / 32; off <<= 1) v = xyzz_add_pair(v, off);
+        for (int off = 1; off < (int)(blockDim.x / 32); off <<= 1) v = xyzz_add_pair(v, off);
         if (threadIdx.x == 0) out[g] = v;
     }
 }
@@ -380,7 +415,7 @@ __global__ void __launch_bounds__(256) k_xyzz_sum(const xyzz_t* __restrict__ pts
 
 int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out) {
     const uint32_t nb = 1u << (k.c - 1);
-    DevBuf<uint32_t> counts, offsets, entries;
+    DevBuf<uint32_t> counts, offsets, entries, order;
     DevBuf<xyzz_t> buckets, partial;
     cudaStream_t s = ctx->stream;
     VK_TRY(counts.alloc(ctx, nb + 2));  // [nb] = dropped entries of the optimistic scatter, [nb + 1] = bit-combine ticket
@@ -425,9 +460,17 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         VK_TRY(entries.alloc(ctx, (size_t)cap * nb + (size_t)top_n * top_extra));
         k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, top_n, top_extra, counts, entries, dropped);
         VK_TRY(launch_check(ctx));
+        const uint32_t* order_p = nullptr;
+        if (!getenv("VKZG_MSM_NO_ORDER")) {  // (measurement knob)
+            VK_TRY(order.alloc(ctx, nb));
+            k_msm_order<<<1, 1024, 0, s>>>(counts, nb, order);
+            VK_TRY(launch_check(ctx));
+            order_p = order;
+        }
         {
             KernelTimer timer(ctx);
-            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, top_n, top_extra, buckets, dropped, 0);
+            k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, counts, entries, nb, P, cap, top_n, top_extra, buckets, dropped, 0,
+                                                                    order_p);
         }
         VK_TRY(launch_check(ctx));
         gate = dropped;
@@ -451,10 +494,10 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         VK_TRY(launch_check(ctx));
     }
     if (gate) {  // (the optimistic launch above is the timed one)
-        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, 0, 0, buckets, gate, 1);
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, 0, 0, buckets, gate, 1, nullptr);
     } else {
         KernelTimer timer(ctx);
-        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, 0, 0, buckets, gate, 1);
+        k_msm_bucket<<<ceil_div_u64(threads, 128), 128, 0, s>>>(k.table, offsets, entries2, nb, P, 0, 0, 0, buckets, gate, 1, nullptr);
     }
     VK_TRY(launch_check(ctx));
     uint32_t rblocks;
@@ -477,7 +520,13 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
             split_l = nb / split_h;
             n_el = split_h + split_l;
             VK_TRY(groups.alloc(ctx, n_el));
-            k_msm_group_sums<<<n_el, GS_THREADS, 0, s>>>(buckets, split_h, split_l, groups);
+            static int gs_threads = -1;
+            if (gs_threads < 0) {
+                const char* e = getenv("VKZG_MSM_GS");  // measurement knob: threads per group sum (32 / 64 / 128)
+                gs_threads = e ? atoi(e) : 0;
+                if (gs_threads != 32 && gs_threads != 64 && gs_threads != 128) gs_threads = GS_THREADS;
+            }
+            k_msm_group_sums<<<n_el, gs_threads, 0, s>>>(buckets, split_h, split_l, groups);
             VK_TRY(launch_check(ctx));
             elems = groups;
             bits = lg;                                  // weights (h - 1) l < 2^(c-1) and l <= 2^((c-1)/2)
