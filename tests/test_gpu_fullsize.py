@@ -78,6 +78,23 @@ def test_msm_2_20_linearity(eng):
     assert (eng.msm(key, orc.field_op(0, "mul", s1, np.tile(kk, (n, 1)))) == orc.g1_mul(m1, kk[0])).all()
     # a prefix against the oracle's bucket method
     assert (eng.msm(key, s1[:5000]) == orc.msm(pts[:5000], s1[:5000], mode="pippenger")).all()
+    # the whole MSM (n >= 2^19: two bucket passes, the second scatter overlapped with the first pass) against the sum of
+    # range MSMs small enough for the single-pass form, cut at points that do not line up with the split
+    d_s = torch.from_numpy(s1).cuda()
+    d_out = torch.empty((1, 64), dtype=torch.uint8, device="cuda")
+    acc = np.zeros(64, dtype=np.uint8)
+    cuts = [0, 200_000, 262_144 + 77, 600_001, 850_000, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        eng.msm_dev(key, d_s[a:b], b - a, d_out, first=a)
+        eng.sync()
+        acc = orc.g1_add(acc, d_out.cpu().numpy()[0])
+    assert (acc == m1).all()
+    # one scalar changed in each part of the split: the result moves by exactly (s' - s) P_j
+    for j in (5, n // 4 - 1, n // 4 + 3, n - 1):
+        t = s1.copy()
+        t[j] = s2[j]
+        diff = orc.field_op(0, "sub", s2[j:j + 1], s1[j:j + 1])[0]
+        assert (eng.msm(key, t) == orc.g1_add(m1, orc.g1_mul(pts[j], diff))).all(), j
     key.free()
 
 

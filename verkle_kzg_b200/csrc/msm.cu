@@ -430,7 +430,7 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         const char* e = getenv("VKZG_MSM_P");
         p_env = e ? atoi(e) : 0;
     }
-    while (P < 32 && avg / (P * 2) >= 48) P *= 2;  // ~64 additions per lane (measured best on B200: P = 8 at n = 2^20)
+    while (P < 32 && avg / (P * 2) >= 48) P *= 2;  // 48 .. 95 additions per lane (P = 4 at n = 2^20, c = 17: 60 per lane; P = 2: -1 %, P = 8: -3 %)
     // (the top window is short — 7 bits at c = 13 — so the first ~100 buckets also receive n / 2^7 top digits each, 4x the mean
     //  list: with P = 32 their lanes still finish inside the kernel's throughput-bound time; striping those lists over extra
     //  lane groups was measured: it rescues P = 8 / 16 (1.03 -> 0.63 ms at 2^16) but the best configuration stays P = 32.)
@@ -452,6 +452,10 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         uint64_t per = n / (r_top ? r_top : 1);
         top_extra = (uint32_t)(per + per / 4 + 64);
     }
+    // (A split form — scatter the first 1/k of the points, then scatter the rest on a high-priority side stream UNDER the bucket
+    //  pass of the first part, second bucket pass on top of the first one's sums — was built and measured at 2^20 / 2^19 points,
+    //  k = 2 .. 8: 3.00 - 3.26 ms against 2.90 ms unsplit (2^19: 1.77 - 2.08 against 1.63).  The two shorter bucket passes lose
+    //  more to their partial last waves and to the scatter's CTAs than the 0.15 ms of hidden scatter returns.  Not kept.)
     const bool optimistic = n >= (1u << 12) && cap64 * nb + (uint64_t)top_n * top_extra < (1ull << 31) && !getenv("VKZG_MSM_TWO_PASS");
     const uint32_t* gate = nullptr;
     if (optimistic) {
