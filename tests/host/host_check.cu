@@ -15,18 +15,18 @@ static void sta(uint8_t* p, const affine_t& a) { st(p, a.x); st(p + 32, a.y); }
 
 extern "C" {
 
-// tag 0 = Fr, 1 = Fq ; op 0 add 1 sub 2 mul 3 inv (binary Euclid) 4 from_mont 5 to_mont 6 neg 7 inv (Fermat) 8 lazy mul (inputs < 2p) 9 lazy sub 10 lazy add 11 lazy square (input <= 2p) 12 lazy square, raw result (must stay below 2p) — outputs canonicalised
+// tag 0 = Fr, 1 = Fq ; op 0 add 1 sub 2 mul 3 inv (binary Euclid) 4 from_mont 5 to_mont 6 neg 7 inv (Fermat) 8 lazy mul (inputs < 2p) 9 lazy sub 10 lazy add 11 lazy square (input <= 2p) 12 lazy square, raw result (must stay below 2p) 13 / 14 Karatsuba lazy product, canonical / raw — outputs canonicalised
 int hc_field_op(int tag, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) {
         fp_t x = ld(a + 32 * i), y = b ? ld(b + 32 * i) : x, r;
         if (tag == 0) {
             r = op == 0 ? fp_add<S>(x, y) : op == 1 ? fp_sub<S>(x, y) : op == 2 ? fp_mul<S>(x, y) : op == 3 ? fp_inv<S>(x)
               : op == 4 ? fp_from_mont<S>(x) : op == 5 ? fp_to_mont<S>(x) : op == 7 ? fp_inv_fermat<S>(x)
-              : op == 8 ? fp_canon<S>(fp_mul_lazy<S>(x, y)) : op == 9 ? fp_canon<S>(fp_sub_lazy<S>(x, y)) : op == 10 ? fp_canon<S>(fp_add_lazy<S>(x, y)) : op == 11 ? fp_canon<S>(fp_sqr_lazy<S>(x)) : op == 12 ? fp_sqr_lazy<S>(x) : fp_neg<S>(x);
+              : op == 8 ? fp_canon<S>(fp_mul_lazy<S>(x, y)) : op == 9 ? fp_canon<S>(fp_sub_lazy<S>(x, y)) : op == 10 ? fp_canon<S>(fp_add_lazy<S>(x, y)) : op == 11 ? fp_canon<S>(fp_sqr_lazy<S>(x)) : op == 12 ? fp_sqr_lazy<S>(x) : op == 13 ? fp_canon<S>(fp_mul_lazy_kara<S>(x, y)) : op == 14 ? fp_mul_lazy_kara<S>(x, y) : fp_neg<S>(x);
         } else {
             r = op == 0 ? fp_add<Q>(x, y) : op == 1 ? fp_sub<Q>(x, y) : op == 2 ? fp_mul<Q>(x, y) : op == 3 ? fp_inv<Q>(x)
               : op == 4 ? fp_from_mont<Q>(x) : op == 5 ? fp_to_mont<Q>(x) : op == 7 ? fp_inv_fermat<Q>(x)
-              : op == 8 ? fp_canon<Q>(fp_mul_lazy<Q>(x, y)) : op == 9 ? fp_canon<Q>(fp_sub_lazy<Q>(x, y)) : op == 10 ? fp_canon<Q>(fp_add_lazy<Q>(x, y)) : op == 11 ? fp_canon<Q>(fp_sqr_lazy<Q>(x)) : op == 12 ? fp_sqr_lazy<Q>(x) : fp_neg<Q>(x);
+              : op == 8 ? fp_canon<Q>(fp_mul_lazy<Q>(x, y)) : op == 9 ? fp_canon<Q>(fp_sub_lazy<Q>(x, y)) : op == 10 ? fp_canon<Q>(fp_add_lazy<Q>(x, y)) : op == 11 ? fp_canon<Q>(fp_sqr_lazy<Q>(x)) : op == 12 ? fp_sqr_lazy<Q>(x) : op == 13 ? fp_canon<Q>(fp_mul_lazy_kara<Q>(x, y)) : op == 14 ? fp_mul_lazy_kara<Q>(x, y) : fp_neg<Q>(x);
         }
         st(out + 32 * i, r);
     }

@@ -36,7 +36,7 @@ def _operands():
     return [int.from_bytes(rng.bytes(32), "little") % (2 * mod + 1) for _ in range(20000)] + edge
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("iters", [1, 2, 7])
 def test_square_chain_matches_python(eng, mode, iters):
     """x <- x^(2^iters) in Montgomery arithmetic, operands anywhere in [0, 2p] (the lazy range of the accumulation loops)"""
@@ -66,5 +66,42 @@ def test_square_equals_product_at_scale(eng):
     b = a.clone()
     eng.probe_fq_sqr_dev(a, a.shape[0], 64, 0)
     eng.probe_fq_sqr_dev(b, b.shape[0], 64, 1)
+    eng.sync()
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("iters", [1, 3])
+def test_product_chain_matches_python(eng, mode, iters):
+    """x <- x b^iters with b = x's halves swapped (both signs of the Karatsuba middle term occur), general (3) / Karatsuba (4)"""
+    import torch
+    mod = orc.P_MOD
+    xs = _operands()
+    M128 = (1 << 128) - 1
+    # operands whose halves are equal or differ in the lowest bits only, and all-ones halves
+    xs += [(h << 128) | h for h in (0, 1, M128 >> 3, 12345)] + [((M128 >> 3) << 128) | M128, (1 << 128) | 2, (2 << 128) | 1]
+    d = torch.from_numpy(_raw(xs)).cuda()
+    eng.probe_fq_sqr_dev(d, len(xs), iters, mode)
+    eng.sync()
+    got = [int.from_bytes(bytes(r), "little") for r in d.cpu().numpy()]
+    rinv = pow(orc.MONT_R, -1, mod)
+    want = []
+    for x in xs:
+        b = ((x & M128) << 128 | (x >> 128)) & ((1 << 254) - 1)
+        for _ in range(iters):
+            x = x * b * rinv % mod
+        want.append(x)
+    assert got == want
+
+
+def test_karatsuba_equals_general_product_at_scale(eng):
+    import torch
+    g = torch.Generator().manual_seed(77)
+    raw = torch.randint(0, 256, (1 << 20, 32), dtype=torch.uint8, generator=g)
+    raw[:, 31] &= 0x3F
+    a = raw.cuda()
+    b = a.clone()
+    eng.probe_fq_sqr_dev(a, a.shape[0], 33, 3)
+    eng.probe_fq_sqr_dev(b, b.shape[0], 33, 4)
     eng.sync()
     assert torch.equal(a, b)

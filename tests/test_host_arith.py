@@ -86,6 +86,41 @@ def test_lazy_reduction_ops(hc, tag, mod):
 
 
 @pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
+def test_karatsuba_product(hc, tag, mod):
+    """fp_mul_lazy_kara: three 4 x 4-limb products glued on the ALU pipe, then the reduction rows alone; operands anywhere in
+    [0, 2p], raw result below 2p.  The operand pairs stress both signs of (a1 - a0)(b1 - b0), equal halves and all-ones limbs."""
+    rng = np.random.default_rng(900 + tag)
+    half = lambda lo, hi: (hi << 128) | lo
+    M128 = (1 << 128) - 1
+    edge = [0, 1, mod - 1, mod, mod + 1, 2 * mod - 1, 2 * mod, (1 << 254) - 1, (1 << 254), mod + (1 << 253), 2 * mod - (1 << 32), (1 << 128), M128,
+            half(M128, 0), half(0, (2 * mod) >> 128), half(M128, (2 * mod) >> 128) if half(M128, (2 * mod) >> 128) <= 2 * mod else 0,
+            half(12345, 12345), half(M128, M128 >> 3), half(M128 >> 3, M128 >> 3), half(1, 0), half(0, 1), half(1 << 127, 1 << 125)]
+    edge = [e for e in edge if e <= 2 * mod]
+    xs, ys = [], []
+    for e in edge:
+        for f in edge:
+            xs.append(e)
+            ys.append(f)
+    for _ in range(4000):
+        xs.append(int.from_bytes(rng.bytes(32), "little") % (2 * mod + 1))
+        ys.append(int.from_bytes(rng.bytes(32), "little") % (2 * mod + 1))
+    for _ in range(500):   # halves that differ only in their low limbs: tiny |a1 - a0|, both signs
+        h = int.from_bytes(rng.bytes(16), "little") >> 3
+        d1, d2 = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+        xs.append(half(h, max(h - d1, 0)))
+        ys.append(half(max(h - d2, 0), h))
+    raw = lambda v: np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in v), dtype=np.uint8).reshape(-1, 32).copy()
+    a, b = raw(xs), raw(ys)
+    rinv = pow(orc.MONT_R, -1, mod)
+    val = lambda buf: [int.from_bytes(bytes(r), "little") for r in buf]
+    want = [(x * y * rinv) % mod for x, y in zip(xs, ys)]
+    assert val(_op(hc, tag, 13, a, b)) == want
+    got = val(_op(hc, tag, 14, a, b))
+    assert all(g < 2 * mod for g in got)
+    assert [g % mod for g in got] == want
+
+
+@pytest.mark.parametrize("tag,mod", [(0, orc.R_MOD), (1, orc.P_MOD)])
 def test_dedicated_square(hc, tag, mod):
     """fp_sqr_lazy: a^2 / R with 36 instead of 64 limb products (doubled off-diagonal rows interleaved with the reduction),
     operand anywhere in [0, 2p]; the raw result must respect the [0, 2p) invariant of the hot loops"""

@@ -365,14 +365,20 @@ __global__ void __launch_bounds__(256) k_probe_fq_mul(fp_t* x, const fp_t* y, ui
 }
 
 // x <- x^(2^iters) through the hot loops' out-of-line multipliers: MODE 0 the dedicated square (fp_sqr_lazy), 1 the general
-// lazy product on equal operands.  The device-side check of the square's carry chains and its throughput probe.
+// lazy product on equal operands, 2 the Karatsuba product on equal operands; 3 / 4: x <- x b^iters (general / Karatsuba).  The device-side check of the square's carry chains and its throughput probe.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_probe_fq_sqr(fp_t* x, uint64_t n, uint32_t iters) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp_t a = fp_load(x + i);
+    fp_t a = fp_load(x + i), b;
+    // modes 3 / 4: a <- a * b with b = the operand's halves swapped (below 2^254)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b.l[k] = a.l[(k + 4) & 7];
+    b.l[7] &= 0x3fffffffu;
 #pragma unroll 1
-    for (uint32_t k = 0; k < iters; ++k) a = MODE == 0 ? fp_sqr_lazy_ni<Q>(a) : fp_mul_lazy_ni<Q>(a, a);
+    for (uint32_t k = 0; k < iters; ++k)
+        a = MODE == 0 ? fp_sqr_lazy_ni<Q>(a) : MODE == 1 ? fp_mul_lazy_ni<Q>(a, a) : MODE == 2 ? fp_mul_lazy_kara_ni<Q>(a, a)
+          : MODE == 3 ? fp_mul_lazy_ni<Q>(a, b) : fp_mul_lazy_kara_ni<Q>(a, b);
     fp_store(x + i, fp_canon<Q>(a));
 }
 
@@ -460,11 +466,15 @@ int32_t vkzg_probe_fq_mul_dev(vkzg_ctx* ctx, vkzg_fq* d_x, const vkzg_fq* d_y, u
 
 int32_t vkzg_probe_fq_sqr_dev(vkzg_ctx* ctx, vkzg_fq* d_x, uint64_t n, uint32_t iters, uint32_t mode) {
     VK_TRY(ctx_check(ctx));
-    if (!d_x || !n || mode > 1) return VKZG_ERR_ARG;
-    if (mode == 0)
-        k_probe_fq_sqr<0><<<ceil_div_u64(n, 256), 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters);
-    else
-        k_probe_fq_sqr<1><<<ceil_div_u64(n, 256), 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters);
+    if (!d_x || !n || mode > 4) return VKZG_ERR_ARG;
+    const uint32_t g = (uint32_t)ceil_div_u64(n, 256);
+    switch (mode) {
+        case 0: k_probe_fq_sqr<0><<<g, 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters); break;
+        case 1: k_probe_fq_sqr<1><<<g, 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters); break;
+        case 2: k_probe_fq_sqr<2><<<g, 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters); break;
+        case 3: k_probe_fq_sqr<3><<<g, 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters); break;
+        default: k_probe_fq_sqr<4><<<g, 256, 0, ctx->stream>>>((fp_t*)d_x, n, iters); break;
+    }
     return launch_check(ctx);
 }
 
