@@ -267,11 +267,15 @@ int32_t vkzg_msm_dev(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* d_scalars, u
 int32_t vkzg_msm(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* scalars, uint64_t n, vkzg_g1_affine* out) {
     VK_TRY(ctx_check(ctx));
     if (!out || (n && !scalars)) return VKZG_ERR_ARG;
+    Key* k = ctx->key(key_id);
+    if (!k || k->kind != VKZG_KEY_MSM) return VKZG_ERR_ARG;
+    if (n > k->n) return VKZG_ERR_RANGE;
     DevBuf<fp_t> ds;
     DevBuf<affine_t> dout;
-    VK_TRY(upload(ctx, ds, scalars, n));
+    VK_TRY(ds.alloc(ctx, n));
     VK_TRY(dout.alloc(ctx, 1));
-    VK_TRY(vkzg_msm_dev(ctx, key_id, (const vkzg_fr*)ds.p, n, (vkzg_g1_affine*)dout.p));
+    // the scalars cross PCIe in pieces and every piece is scattered into the bucket lists while the next one is in flight
+    VK_TRY(msm_large(ctx, *k, 0, ds.p, n, dout.p, (const fp_t*)scalars));
     VK_TRY(download(ctx, out, dout.p, 1));
     return stream_sync(ctx);
 }

@@ -413,7 +413,10 @@ __global__ void __launch_bounds__(256) k_xyzz_sum(const xyzz_t* __restrict__ pts
     if (threadIdx.x == 0) out[0] = sh[0];
 }
 
-int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out) {
+// h_scalars != nullptr: d_scalars is an allocated but EMPTY device buffer and the scalars are still in host memory — they are
+// uploaded in pieces on the copy stream and every piece is scattered as soon as it has arrived (the scatter of piece k runs
+// under the upload of piece k + 1; the cursors and lists are sized for the whole MSM, so the pieces simply append).
+int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out, const fp_t* h_scalars) {
     const uint32_t nb = 1u << (k.c - 1);
     DevBuf<uint32_t> counts, offsets, entries, order;
     DevBuf<xyzz_t> buckets, partial;
@@ -462,8 +465,27 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         const uint32_t cap = (uint32_t)cap64;
         uint32_t* dropped = counts.p + nb;
         VK_TRY(entries.alloc(ctx, (size_t)cap * nb + (size_t)top_n * top_extra));
-        k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, top_n, top_extra, counts, entries, dropped);
-        VK_TRY(launch_check(ctx));
+        if (h_scalars && n >= (1u << 17)) {
+            ChunkedUpload up(ctx);
+            VK_TRY(up.init());
+            const uint64_t piece = ((n + 3) / 4 + 255) & ~255ull;
+            for (uint64_t p0 = 0; p0 < n; p0 += piece) {
+                const uint64_t np = n - p0 < piece ? n - p0 : piece;
+                VK_TRY(up.copy(const_cast<fp_t*>(d_scalars) + p0, h_scalars + p0, np * sizeof(fp_t)));
+                VK_TRY(up.publish());
+                k_msm_scatter_fixed<<<ceil_div_u64(np, 256), 256, 0, s>>>(d_scalars + p0, np, k.c, k.W, k.n, first + p0, cap, top_n, top_extra,
+                                                                        counts, entries, dropped);
+                VK_TRY(launch_check(ctx));
+            }
+            h_scalars = nullptr;
+        } else {
+            if (h_scalars) {
+                VK_CUDA(cudaMemcpyAsync(const_cast<fp_t*>(d_scalars), h_scalars, n * sizeof(fp_t), cudaMemcpyHostToDevice, s));
+                h_scalars = nullptr;
+            }
+            k_msm_scatter_fixed<<<gb, 256, 0, s>>>(d_scalars, n, k.c, k.W, k.n, first, cap, top_n, top_extra, counts, entries, dropped);
+            VK_TRY(launch_check(ctx));
+        }
         const uint32_t* order_p = nullptr;
         if (!getenv("VKZG_MSM_NO_ORDER")) {  // (measurement knob)
             VK_TRY(order.alloc(ctx, nb));
@@ -485,6 +507,7 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     //      ~10 us of empty launches instead of a device -> host -> device round trip).  Its n * W entry buffer (64 MB per
     //      2^20 points) comes from the context's pool like everything else.
     DevBuf<uint32_t> entries2;
+    if (h_scalars && n) VK_CUDA(cudaMemcpyAsync(const_cast<fp_t*>(d_scalars), h_scalars, n * sizeof(fp_t), cudaMemcpyHostToDevice, s));
     VK_TRY(offsets.alloc(ctx, nb + 1));
     VK_TRY(entries2.alloc(ctx, (size_t)n * k.W));
     if (n) {
@@ -539,6 +562,8 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
         const uint32_t slices = (n_el + BS_SLICE - 1) / BS_SLICE;
         rblocks = bits * slices;
         VK_TRY(partial.alloc(ctx, (size_t)rblocks + 1 + bits));
+        // (a thread per element for the single slice of the two-level form — 256 or 512 threads — was measured: 1 - 4 % slower,
+        //  the wider shared-memory tree costs more than the <= 4 serial additions it removes)
         k_msm_bitsums<<<dim3(slices, bits), BS_THREADS, 0, s>>>(elems, n_el, slices, split_h, split_l, partial);
         VK_TRY(launch_check(ctx));
         k_msm_bitcombine<<<bits, 32, 0, s>>>(partial, bits, slices, partial.p + rblocks + 1, counts.p + nb + 1, partial.p + rblocks);

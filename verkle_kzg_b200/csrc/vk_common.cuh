@@ -261,7 +261,8 @@ int32_t poly_batch(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, u
 int32_t kzg_open_core(vkzg_ctx* ctx, const Key& k, const fp_t* d_f, uint32_t len, uint32_t domain_n, const fp_t* d_points,
                       uint64_t B, affine_t* d_proof, fp_t* d_y, bool check_err);
 int32_t var_base_msm(vkzg_ctx* ctx, const affine_t* d_points, const fp_t* d_scalars, uint64_t n, affine_t* d_out);
-int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out);
+int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_scalars, uint64_t n, affine_t* d_out,
+                  const fp_t* h_scalars = nullptr);
 int32_t g1_sum(vkzg_ctx* ctx, const affine_t* d_points, uint64_t n, affine_t* d_out);
 int32_t to_data_item(vkzg_ctx* ctx, const affine_t* d_points, uint64_t n, fp_t* d_out);
 
