@@ -74,6 +74,12 @@ def main():
         for i in range(Bk):
             epf, ey, ok = orc.kzg_prove(srs, fk[i], zkb[i])
             assert ok and (pf[i] == epf).all() and (yk[i] == ey).all(), ("kzg", N, c, zk[i])
+        if it % 4 == 1:   # all-points prover (kzg/mod.rs:200-235 by its contract): entry i == prove_point at i
+            pa, ya = eng.kzg_prove_all_batch(kk, fk[:2])
+            for b_ in range(min(2, Bk)):
+                for i in {0, N - 1, int(rng.integers(0, N))}:
+                    epf, ey, ok = orc.kzg_prove(srs, fk[b_], orc.fr_to_buf([i])[0])
+                    assert ok and (pa[b_, i] == epf).all() and (ya[b_, i] == ey).all(), ("kzg-all", N, c, i)
         kk.free()
         # native host tree against the oracle's replay of the same insertion sequence, random flatten mode
         if tree_key is not None and it % 4 == 0:
