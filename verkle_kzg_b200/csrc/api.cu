@@ -308,9 +308,8 @@ int32_t vkzg_commit_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr* scalars
     // chunks of the batch upload on the copy stream while the previous chunk is committed
     ChunkedUpload up(ctx);
     VK_TRY(up.init());
-    const uint64_t chunk = pipeline_chunk(B);
-    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
-        uint64_t nb = B - b0 < chunk ? B - b0 : chunk;
+    for (uint64_t b0 = 0, nb = 0; b0 < B; b0 += nb) {
+        nb = pipeline_piece(B, b0);
         VK_TRY(up.copy(ds.p + b0 * w, (const fp_t*)scalars + b0 * w, nb * w * sizeof(fp_t)));
         VK_TRY(up.publish());
         VK_TRY(fixed_base_msm(ctx, *k, ds.p + b0 * w, w, nb, 0, 0xffffffffu, acc.p + b0));

@@ -656,9 +656,8 @@ int32_t vkzg_ipa_commit_prove_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_f
     VK_TRY(dy.alloc(ctx, B));
     ChunkedUpload up(ctx);
     VK_TRY(up.init());
-    const uint64_t chunk = pipeline_chunk(B);
-    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
-        uint64_t nb = B - b0 < chunk ? B - b0 : chunk;
+    for (uint64_t b0 = 0, nb = 0; b0 < B; b0 += nb) {
+        nb = pipeline_piece(B, b0);
         VK_TRY(up.copy(da.p + b0 * N, (const fp_t*)a + b0 * N, nb * N * sizeof(fp_t)));
         VK_TRY(up.publish());
         VK_TRY(fixed_base_msm(ctx, *k, da.p + b0 * N, N, nb, 0, 0xffffffffu, acc.p + b0));

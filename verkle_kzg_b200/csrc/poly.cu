@@ -409,9 +409,8 @@ int32_t vkzg_kzg_commit_open_batch(vkzg_ctx* ctx, uint32_t key_id, const vkzg_fr
     VK_TRY(acc.alloc(ctx, B));
     ChunkedUpload up(ctx);
     VK_TRY(up.init());
-    const uint64_t chunk = pipeline_chunk(B);
-    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
-        uint64_t nb = B - b0 < chunk ? B - b0 : chunk;
+    for (uint64_t b0 = 0, nb = 0; b0 < B; b0 += nb) {
+        nb = pipeline_piece(B, b0);
         VK_TRY(up.copy(df.p + b0 * len, (const fp_t*)f + b0 * len, nb * len * sizeof(fp_t)));
         VK_TRY(up.publish());
         VK_TRY(fixed_base_msm(ctx, *k, df.p + b0 * len, len, nb, 0, 0xffffffffu, acc.p + b0));

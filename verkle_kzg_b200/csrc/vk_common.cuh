@@ -218,12 +218,23 @@ struct ChunkedUpload {
     }
 };
 
-// chunks must stay large enough to fill the GPU (>= 4096 one-warp jobs) — smaller ones lose more to partial waves
-// than the overlap wins
-static inline uint64_t pipeline_chunk(uint64_t B) {
-    if (B < 8192) return B;
-    uint64_t c = (B + 3) / 4;
-    return c < 4096 ? 4096 : c;
+// Pieces of a pipelined batch upload (piece k is committed while piece k + 1 crosses PCIe).  The first piece is what the GPU
+// waits for and every piece is a kernel launch with its own partial last wave, so the schedule is geometric — B/16, 3B/16, the
+// rest in ONE launch: a width-256 commit computes ~3.5x longer than its scalars take to arrive, each piece's upload hides under
+// the piece before it (2^14 commits from host buffers: see DESIGN.md section 4; VKZG_PIPE_UNIFORM=1 restores four equal pieces).
+static inline uint64_t pipeline_piece(uint64_t B, uint64_t b0) {
+    if (B < 8192) return B - b0;
+    static int uniform = -1;
+    if (uniform < 0) uniform = getenv("VKZG_PIPE_UNIFORM") ? 1 : 0;
+    uint64_t n;
+    if (uniform) {
+        n = (B + 3) / 4;
+        if (n < 4096) n = 4096;
+    } else {
+        const uint64_t first = B / 16, second = 3 * B / 16;
+        n = b0 == 0 ? first : (b0 == first ? second : B - b0);
+    }
+    return n < B - b0 ? n : B - b0;
 }
 
 static inline uint32_t ceil_div_u64(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
