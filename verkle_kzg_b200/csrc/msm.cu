@@ -3,13 +3,15 @@
 // The key holds T[w][i] = 2^(c w) * P_i, so every signed c-bit digit of every scalar lands in ONE shared
 // set of 2^(c-1) buckets (no per-window bucket sets, no final doubling chain):
 //     sum_i s_i P_i = sum_b (b + 1) * B_b ,   B_b = sum over digits of magnitude b + 1 of +-T[w][i].
-//   1. k_msm_count    one thread per scalar: Montgomery -> canonical, signed recode, histogram of buckets
-//   2. k_scan         exclusive prefix sum of the bucket sizes
-//   3. k_msm_scatter  counting-sort scatter of (table index, sign) entries into bucket order
-//   4. k_msm_bucket   P lanes per bucket (P adjacent lanes, interleaved slices -> equal work), 64-byte
+//   1. k_msm_scatter_fixed   one thread per scalar: Montgomery -> canonical, signed recode, every digit appended to the
+//                     fixed-capacity list of its bucket (one pass; an overflow is counted on the device and the exact
+//                     counting sort — k_msm_digits x2 + k_scan — enqueued behind it runs only then)
+//   2. k_msm_order    buckets in order of decreasing list length (the lanes of a warp walk lists of equal length)
+//   3. k_msm_bucket   P lanes per bucket (P adjacent lanes, interleaved slices -> equal work), 64-byte
 //                     vectorised gathers one entry ahead of the mixed addition, shuffle-tree fold of the
 //                     P partial sums
-//   5. k_msm_bitsums + k_msm_bitcombine   weighted bucket sum, bit-parallel (see below), then the common normalisation
+//   4. weighted bucket sum: k_msm_bitsums + k_msm_bitcombine (bit-parallel) up to 4096 buckets, above that k_msm_group_sums
+//      (h + l plain row / column sums) followed by the same two kernels over h + l elements; then the common normalisation
 // The order in which a bucket's points are added is not deterministic (atomics), the result is: it leaves
 // the device in canonical affine form.
 #include "vk_common.cuh"
@@ -354,8 +356,8 @@ __global__ void __launch_bounds__(GS_THREADS) k_msm_group_sums(const xyzz_t* __r
     }
 }
 
-// ---- running-sum form of the weighted bucket sum: less work (2 additions per bucket), longer chain — used for large bucket
-//      sets (nb > 8192), where the bit-parallel form above is bound by its 16x redundant additions, not by its depth
+// ---- running-sum form of the weighted bucket sum: 2 additions per bucket like the two-level form, but a longer chain on few
+//      warps — the round-1 tail for large bucket sets, kept behind VKZG_MSM_TAIL=2 as the baseline of profiles/r02_msm_tail_sweep.txt
 __device__ __noinline__ xyzz_t xyzz_mul_small(const xyzz_t p, uint32_t k) {
     xyzz_t acc = xyzz_inf();
     if (k == 0) return acc;
