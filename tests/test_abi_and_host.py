@@ -316,3 +316,34 @@ def test_bulk_load_on_host_threads_equals_the_sequential_insertion(vk, mode, n, 
         assert d["status"] == -3 and 0 < d["done"] < n
     else:
         assert d["status"] == 0 and d["done"] == n
+
+
+def test_two_level_weighted_bucket_sum_identity():
+    """The large-MSM tail (csrc/msm.cu, form 3): with b = hi * l + lo,
+        sum_b (b + 1) B_b = l * sum_hi hi S_hi + sum_lo (lo + 1) T_lo,   S_hi = row sums, T_lo = column sums,
+    and the h + l group sums with weights msm_weight(e) = e * l (e < h) | e - h + 1 fit the bit count the host code passes to the
+    bit-parallel kernels.  Integers stand in for group elements (the identity is linear)."""
+    rng = np.random.default_rng(31)
+    for c in range(5, 21):
+        lg = c - 1
+        nb = 1 << lg
+        h = 1 << ((lg + 1) // 2)
+        l = nb // h
+        assert h * l == nb
+        n = min(nb, 4096)                     # a sparse random bucket set is enough for a linear identity
+        idx = rng.choice(nb, n, replace=False)
+        val = [int(v) for v in rng.integers(1, 1 << 62, n)]
+        want = sum((int(b) + 1) * v for b, v in zip(idx, val))
+        S, T = [0] * h, [0] * l
+        for b, v in zip(idx, val):
+            S[int(b) // l] += v
+            T[int(b) % l] += v
+        groups = S + T
+        weight = lambda e: e * l if e < h else e - h + 1
+        bits = lg
+        while (l >> bits) != 0:
+            bits += 1
+        assert all(weight(e) < (1 << bits) for e in range(h + l))
+        # bit-parallel evaluation as k_msm_bitsums / k_msm_bitcombine do it: sum_j 2^j * (sum of the groups whose weight has bit j)
+        got = sum((1 << j) * sum(g for e, g in enumerate(groups) if (weight(e) >> j) & 1) for j in range(bits))
+        assert got == want, c
