@@ -440,8 +440,18 @@ int32_t msm_large(vkzg_ctx* ctx, const Key& k, uint64_t first, const fp_t* d_sca
     //  list: with P = 32 their lanes still finish inside the kernel's throughput-bound time; striping those lists over extra
     //  lane groups was measured: it rescues P = 8 / 16 (1.03 -> 0.63 ms at 2^16) but the best configuration stays P = 32.)
     // small slices: one lane per bucket leaves most of the GPU idle (2^16 points: 32 K lanes of ~32 dependent additions on
-    // 75 K thread slots) — split the buckets further until the grid fills about two waves, down to ~6 additions per lane
-    while (P < 32 && (uint64_t)nb * P < (uint64_t)ctx->sm_count * 512 * 2 && avg / (P * 2) >= 6) P *= 2;
+    // 75 K thread slots) — split the buckets further until the grid fills ONE wave of lanes (two where the short top window
+    // makes a few buckets several times longer than the rest: their lanes set the kernel's duration), down to ~6 additions per
+    // lane.  Re-measured on the final kernels (profiles/r02_msm_lanes_sweep.txt): 2^17 points P = 8 (0.668 ms; 16: 0.730, 4: 0.721),
+    // 2^18 P = 4 (1.016 ms; 8: 1.054, 2: 1.179), 2^19 P = 2 or 4, 2^16 (c = 13, hot top buckets) P = 32 (0.550 ms; 16: 0.691).
+    const uint32_t top_shift0 = k.c * (k.W - 1);
+    bool hot_top = false;
+    if (top_shift0 < 254 && 254 - top_shift0 < k.c - 1) {
+        const uint32_t r_top0 = top_shift0 >= 224 ? (0x30644e72u >> (top_shift0 - 224)) : 0xffffffffu;
+        hot_top = n / (r_top0 ? r_top0 : 1) > avg / 2;
+    }
+    const uint64_t fill_lanes = (uint64_t)ctx->sm_count * 512 * (hot_top ? 2 : 1);
+    while (P < 32 && (uint64_t)nb * P < fill_lanes && avg / (P * 2) >= 6) P *= 2;
     if (p_env == 1 || p_env == 2 || p_env == 4 || p_env == 8 || p_env == 16 || p_env == 32) P = (uint32_t)p_env;
     uint64_t threads = (uint64_t)nb * P;
     // ---- optimistic single pass (uniform scalars): fixed-capacity bucket lists, no count pass, no scan.  Entries that do
