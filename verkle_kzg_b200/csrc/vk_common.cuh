@@ -221,7 +221,10 @@ struct ChunkedUpload {
 // Pieces of a pipelined batch upload (piece k is committed while piece k + 1 crosses PCIe).  The first piece is what the GPU
 // waits for and every piece is a kernel launch with its own partial last wave, so the schedule is geometric — B/16, 3B/16, the
 // rest in ONE launch: a width-256 commit computes ~3.5x longer than its scalars take to arrive, each piece's upload hides under
-// the piece before it (2^14 commits from host buffers: see DESIGN.md section 4; VKZG_PIPE_UNIFORM=1 restores four equal pieces).
+// the piece before it (2^14 commits from host buffers on one GPU: 1.756 M/s against 1.677 M/s with four equal pieces; what pays is
+// the single big last launch — B/16, 3B/16 followed by quarters measured 1.689 M/s).  The price: when eight ranks share the host's
+// PCIe and memory the 3/4 piece no longer hides (8 x 2^14 commits from host buffers 11.1 M/s against 12.1 M/s) —
+// VKZG_PIPE_UNIFORM=1 restores four equal pieces for such callers.
 static inline uint64_t pipeline_piece(uint64_t B, uint64_t b0) {
     if (B < 8192) return B - b0;
     static int uniform = -1;
