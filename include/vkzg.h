@@ -315,7 +315,7 @@ int32_t vkzg_probe_fq_mul_dev(vkzg_ctx* ctx, vkzg_fq* d_x, const vkzg_fq* d_y, u
 /* x <- x^(2^iters) (Montgomery form; any raw value <= 2p in, canonical out) on each of n elements in place through the hot
  * loops' multipliers: mode 0 = the dedicated square, 1 = the general product on equal operands, 2 = the Karatsuba product on
  * equal operands; modes 3 / 4: x <- x b^iters with b = x's 128-bit halves swapped and bits 254, 255 cleared, through the general /
- * the Karatsuba product (csrc/field.cuh) */
+ * the Karatsuba product (csrc/field.cuh, csrc/field_kara.cuh) */
 int32_t vkzg_probe_fq_sqr_dev(vkzg_ctx* ctx, vkzg_fq* d_x, uint64_t n, uint32_t iters, uint32_t mode);
 /* independent 32x32+64 multiply-accumulate chains on every SM; returns MAC32 issued (kind: 0 = mad.wide.u32,
  * 1 = mad.lo.u32, 2 = mad.wide + carry chain, 3 = fma.rn.f64) */

@@ -3,6 +3,7 @@
 // a GPU.  The carry-chain primitives are emulated on the host (see field.cuh); everything above them is
 // the same code the device runs.
 #include "../../verkle_kzg_b200/csrc/hash.cuh"
+#include "../../verkle_kzg_b200/csrc/field_kara.cuh"
 #include <cstring>
 #include <vector>
 

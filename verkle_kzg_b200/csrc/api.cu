@@ -1,6 +1,7 @@
 // C ABI of libvkzg.so (include/vkzg.h): context / key management, the M1 + D1 entry points and the
 // measurement probes.  The scheme-level entry points live in ipa.cu, poly.cu, multiproof.cu, tree.cu.
 #include "vk_common.cuh"
+#include "field_kara.cuh"  // the probe of the Karatsuba product (measured, not used by the kernels)
 
 using namespace vk;
 
