@@ -4,6 +4,7 @@
 // the same code the device runs.
 #include "../../verkle_kzg_b200/csrc/hash.cuh"
 #include "../../verkle_kzg_b200/csrc/field_kara.cuh"
+#include "../../verkle_kzg_b200/csrc/vk_common.cuh"  // host-side plumbing (pipeline_piece)
 #include <cstring>
 #include <vector>
 
@@ -15,6 +16,19 @@ static affine_t lda(const uint8_t* p) { affine_t a; a.x = ld(p); a.y = ld(p + 32
 static void sta(uint8_t* p, const affine_t& a) { st(p, a.x); st(p + 32, a.y); }
 
 extern "C" {
+
+// the pieces a pipelined batch upload of B rows is cut into (vk_common.cuh); returns their count
+int hc_pipeline_pieces(uint64_t B, uint64_t* out, int cap) {
+    int n = 0;
+    for (uint64_t b0 = 0, nb = 0; b0 < B; b0 += nb) {
+        nb = pipeline_piece(B, b0);
+        if (n < cap) out[n] = nb;
+        ++n;
+        if (nb == 0 || n > 64) return -1;
+    }
+    return n;
+}
+
 
 // tag 0 = Fr, 1 = Fq ; op 0 add 1 sub 2 mul 3 inv (binary Euclid) 4 from_mont 5 to_mont 6 neg 7 inv (Fermat) 8 lazy mul (inputs < 2p) 9 lazy sub 10 lazy add 11 lazy square (input <= 2p) 12 lazy square, raw result (must stay below 2p) 13 / 14 Karatsuba lazy product, canonical / raw — outputs canonicalised
 int hc_field_op(int tag, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t n) {

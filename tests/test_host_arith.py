@@ -273,3 +273,18 @@ def test_transcript_walk(hc):
         hc.hc_transcript_ipa(_p(pre), len(prefix), dst.encode(), _p(orc.pts_to_buf([C])), _p(orc.fr_to_buf([z])), _p(orc.fr_to_buf([y])),
                              _p(orc.pts_to_buf([L])), _p(orc.pts_to_buf([R])), _p(wo), _p(xo))
         assert orc.buf_to_fr(wo)[0] == w and orc.buf_to_fr(xo)[0] == x
+
+
+def test_pipeline_pieces_cover_the_batch(hc):
+    """vk_common.cuh: pipeline_piece — the pieces of a pipelined upload are never empty, cover the batch exactly, start small
+    (B/16, 3B/16) and finish in one launch; batches below 8192 rows are one piece"""
+    out = (ctypes.c_uint64 * 64)()
+    hc.hc_pipeline_pieces.argtypes = [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
+    for B in [1, 2, 4095, 8191, 8192, 8193, 8207, 9000, 16384, 16385, 65536, 1_000_003]:
+        n = hc.hc_pipeline_pieces(B, out, 64)
+        pieces = [int(out[i]) for i in range(n)]
+        assert n >= 1 and all(p > 0 for p in pieces) and sum(pieces) == B, (B, pieces)
+        if B < 8192:
+            assert pieces == [B]
+        else:
+            assert pieces == [B // 16, 3 * B // 16, B - B // 16 - 3 * B // 16], (B, pieces)
