@@ -347,3 +347,32 @@ def test_two_level_weighted_bucket_sum_identity():
         # bit-parallel evaluation as k_msm_bitsums / k_msm_bitcombine do it: sum_j 2^j * (sum of the groups whose weight has bit j)
         got = sum((1 << j) * sum(g for e, g in enumerate(groups) if (weight(e) >> j) & 1) for j in range(bits))
         assert got == want, c
+
+
+def test_dedicated_square_row_identity():
+    """The algebra behind fp_sqr_lazy (csrc/field.cuh): with d = 2a as an 8-limb number (a <= 2p < 2^255),
+        a^2 = sum_i a_i * V_i * 2^(32 i),   V_i = [0 .. 0, a_i, d_(i+1) & ~1, d_(i+2), .. , d_7]  (limb j of V_i sits at 2^(32 j))
+    — row i holds its diagonal term and the doubled off-diagonal terms to its right; clearing bit 0 of d_(i+1) removes bit 31 of
+    a_i, which the shift (2a) >> 32(i+1) drags along.  36 limb products instead of 64."""
+    import orc
+    rng = np.random.default_rng(36)
+    M = (1 << 32) - 1
+    vals = [0, 1, 2 * orc.P_MOD, 2 * orc.P_MOD - 1, (1 << 255) - 1, sum(0x80000000 << (32 * i) for i in range(8)) % (1 << 255)]
+    vals += [int.from_bytes(rng.bytes(32), "little") >> 1 for _ in range(500)]
+    products = 0
+    for a in vals:
+        al = [(a >> (32 * i)) & M for i in range(8)]
+        d = 2 * a
+        assert d < (1 << 256)
+        dl = [(d >> (32 * i)) & M for i in range(8)]
+        total = 0
+        products = 0
+        for i in range(8):
+            V = 0
+            for j in range(i, 8):
+                limb = al[i] if j == i else (dl[j] & ~1 if j == i + 1 else dl[j])
+                V += limb << (32 * j)
+                products += 1
+            total += al[i] * V << (32 * i)
+        assert total == a * a
+    assert products == 36
